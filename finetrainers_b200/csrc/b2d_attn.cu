@@ -1,0 +1,592 @@
+// b2d_attn.cu — attention for d_head = 64 on tcgen05 (forward + backward), non-causal, optional additive key bias.
+//
+// Layouts: q,k,v,dq,dk,dv are [B, H, S, 64] bf16 (a head's rows are contiguous 128 B => one TMA box row = one
+// 128B-swizzle row, usable both as a K-major operand (contract over d) and as an MN-major operand (contract over
+// the sequence) from the SAME shared-memory bytes).  out / dout are token-major [B, S, H*64] so that to_out's GEMM
+// consumes them without a transpose; they are addressed through 4-D tensor maps as well.
+//
+// Forward, one CTA per (128-query tile, b, h), two CTAs co-resident per SM (they interleave MMA and softmax phases):
+//   warp 0: TMA producer (Q once, then K_j/V_j ring)      warp 1: MMA issuer + TMEM owner
+//   warps 2-5: one thread per query row.  S = Q K_j^T lands in TMEM; the thread reads its row with tcgen05.ld (no
+//   shuffles needed for row max / row sum), exponentiates in the log2 domain, writes P (bf16) into 128B-swizzled smem;
+//   O += P V_j accumulates in TMEM; O is only rescaled when the running max moved by more than 2^8 (lazy rescale).
+//
+// Backward = delta pre-pass + one templated kernel run twice:
+//   DKV=true : CTA per (key tile j): S^T = K_j Q_i^T, dP^T = V_j dO_i^T, P^T, dS^T -> dV += P^T dO_i, dK += dS^T Q_i
+//   DKV=false: CTA per (query tile i): S = Q_i K_j^T, dP = dO_i V_j^T, dS -> dQ += dS K_j
+// (no atomics, deterministic).
+#include "b2d_internal.h"
+#include "b2d_ptx.cuh"
+
+namespace b2d {
+
+constexpr int ATT_THREADS = 192;
+constexpr int TILE = 128;
+constexpr int HD = 64;
+constexpr int TILE_BYTES = TILE * HD * 2;  // 16 KB
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// byte offset of the 16-byte unit `u` (0..7) of row `r` inside a [rows x 128 B] 128B-swizzled tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int u) { return (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// ================================================================================================
+// forward
+// ================================================================================================
+struct AttnFwdParams {
+    CUtensorMap tmQ, tmK, tmV;
+    const float* key_bias;  // [B, Sk] or null
+    __nv_bfloat16* out;     // [B, Sq, H*64]
+    float* lse;             // [B, H, Sq]
+    int B, H, Sq, Sk;
+    float scale_log2;  // scale * log2(e)
+};
+
+constexpr int FWD_KV_STAGES = 2;
+constexpr int FWD_SMEM = TILE_BYTES /*Q*/ + FWD_KV_STAGES * 2 * TILE_BYTES /*K,V*/ + 2 * TILE_BYTES /*P*/ + 1024 + 256;
+
+__global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sKV = sQ + TILE_BYTES;                        // stage s: K at sKV + s*32K, V at +16K
+    uint8_t* sP = sKV + FWD_KV_STAGES * 2 * TILE_BYTES;    // 2 chunks of [128 x 64] bf16
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TILE_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;   // [2]
+    uint64_t* kv_empty = bars + 3;  // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* p_full = bars + 6;
+    uint64_t* pv_done = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * TILE;
+    const int bh = blockIdx.y;
+    const int b = bh / p.H, h = bh % p.H;
+    const int n_kv = (p.Sk + TILE - 1) / TILE;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmQ);
+        tma_prefetch_desc(&p.tmK);
+        tma_prefetch_desc(&p.tmV);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < FWD_KV_STAGES; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 128);
+        mbar_init(pv_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS = tmem;        // 128 cols
+    const uint32_t tO = tmem + 128;  // 64 cols
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(q_full, TILE_BYTES);
+            tma_load_4d(sQ, &p.tmQ, q_full, 0, h, q0, b);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(&kv_empty[stage], phase ^ 1);
+                mbar_expect_tx(&kv_full[stage], 2 * TILE_BYTES);
+                tma_load_4d(sKV + stage * 2 * TILE_BYTES, &p.tmK, &kv_full[stage], 0, h, j * TILE, b);
+                tma_load_4d(sKV + stage * 2 * TILE_BYTES + TILE_BYTES, &p.tmV, &kv_full[stage], 0, h, j * TILE, b);
+                if (++stage == FWD_KV_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+            mbar_wait(q_full, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t aQ = smem_u32(sQ);
+            const uint32_t aP = smem_u32(sP);
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(&kv_full[stage], phase);
+                tc_fence_after();
+                const uint32_t aK = smem_u32(sKV + stage * 2 * TILE_BYTES);
+                const uint32_t aV = aK + TILE_BYTES;
+                // S = Q K^T   (the previous P V already consumed S's successor state: p_full(j-1) implies S was read)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16(tS, make_sdesc_sw128(aQ + k * 32, 16, 1024), make_sdesc_sw128(aK + k * 32, 16, 1024),
+                             idesc_s, k > 0);
+                umma_commit(s_full);
+                // O += P V
+                mbar_wait(p_full, j & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_f16(tO, make_sdesc_sw128(aP + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
+                             make_sdesc_sw128(aV + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&kv_empty[stage]);
+                umma_commit(pv_done);
+                if (++stage == FWD_KV_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int qd = warp & 3;
+        const int r = qd * 32 + lane;  // row within the tile == TMEM lane
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        const float* kb = p.key_bias ? p.key_bias + (long long)b * p.Sk : nullptr;
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            const int kv0 = j * TILE;
+            // ---- pass 1: row max (log2 domain)
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tS + lane_off + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int col = kv0 + c * 32 + e;
+                    float x = __uint_as_float(v[e]) * p.scale_log2;
+                    if (kb) x += kb[min(col, p.Sk - 1)] * LOG2E;
+                    x = col < p.Sk ? x : -INFINITY;
+                    mx = fmaxf(mx, x);
+                }
+            }
+            // ---- running max with lazy rescale of O
+            float m_use = m_run;
+            if (j == 0) {
+                m_use = mx;
+            } else {
+                const bool need = (mx - m_run) > 8.0f;
+                // P buffer and O are free only once the previous P V has completed
+                mbar_wait(pv_done, (j - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, need)) {
+                    if (need) m_use = mx;
+                    const float alpha = fast_exp2(m_run - m_use);
+                    l_run *= alpha;
+#pragma unroll 1
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t v[32];
+                        tmem_ld32(tO + lane_off + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+                        tmem_st32(tO + lane_off + c * 32, v);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            m_run = m_use;
+            // ---- pass 2: P = exp2(x - m), row sum, bf16 -> swizzled smem
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tS + lane_off + c * 32, v);
+                tmem_ld_wait();
+                float pv[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int col = kv0 + c * 32 + e;
+                    float x = __uint_as_float(v[e]) * p.scale_log2 - m_use;
+                    if (kb) x += kb[min(col, p.Sk - 1)] * LOG2E;
+                    float pe = col < p.Sk ? fast_exp2(x) : 0.f;
+                    pv[e] = pe;
+                    l_run += pe;
+                }
+                uint8_t* chunk = sP + (c >> 1) * TILE_BYTES;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint4 w = make_uint4(pack_bf16x2(pv[u * 8], pv[u * 8 + 1]), pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]),
+                                         pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]), pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]));
+                    *reinterpret_cast<uint4*>(chunk + sw128_off(r, (c & 1) * 4 + u)) = w;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        // ---- epilogue: O / l -> out (token-major), lse
+        mbar_wait(pv_done, (n_kv - 1) & 1);
+        tc_fence_after();
+        const int qrow = q0 + r;
+        const float inv_l = 1.f / l_run;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tO + lane_off + c * 32, v);
+            tmem_ld_wait();
+            if (qrow < p.Sq) {
+                __nv_bfloat16* o = p.out + ((long long)b * p.Sq + qrow) * (p.H * HD) + h * HD + c * 32;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint4 w = make_uint4(
+                        pack_bf16x2(__uint_as_float(v[u * 8]) * inv_l, __uint_as_float(v[u * 8 + 1]) * inv_l),
+                        pack_bf16x2(__uint_as_float(v[u * 8 + 2]) * inv_l, __uint_as_float(v[u * 8 + 3]) * inv_l),
+                        pack_bf16x2(__uint_as_float(v[u * 8 + 4]) * inv_l, __uint_as_float(v[u * 8 + 5]) * inv_l),
+                        pack_bf16x2(__uint_as_float(v[u * 8 + 6]) * inv_l, __uint_as_float(v[u * 8 + 7]) * inv_l));
+                    *reinterpret_cast<uint4*>(o + u * 8) = w;
+                }
+            }
+        }
+        if (qrow < p.Sq) p.lse[((long long)b * p.H + h) * p.Sq + qrow] = m_run * LN2 + logf(l_run);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 256);
+    }
+}
+
+// ================================================================================================
+// backward
+// ================================================================================================
+// delta[b,h,q] = sum_d out[b,q,h,d] * dout[b,q,h,d]     (8 lanes per head-row)
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                                  float* __restrict__ delta, int B, int H, int Sq) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Sq * H * 8;
+    const bool ok = t < total;
+    const long long e0 = (ok ? t : 0) * 8;
+    uint4 a = *reinterpret_cast<const uint4*>(out + e0);
+    uint4 d = *reinterpret_cast<const uint4*>(dout + e0);
+    float acc = bf16_lo(a.x) * bf16_lo(d.x) + bf16_hi(a.x) * bf16_hi(d.x) + bf16_lo(a.y) * bf16_lo(d.y) +
+                bf16_hi(a.y) * bf16_hi(d.y) + bf16_lo(a.z) * bf16_lo(d.z) + bf16_hi(a.z) * bf16_hi(d.z) +
+                bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (ok && (t & 7) == 0) {
+        const long long hr = t >> 3;  // (b*Sq + q)*H + h
+        const int h = (int)(hr % H);
+        const long long bq = hr / H;
+        const int q = (int)(bq % Sq);
+        const int b = (int)(bq / Sq);
+        delta[((long long)b * H + h) * Sq + q] = acc;
+    }
+}
+
+struct AttnBwdParams {
+    CUtensorMap tmX1, tmX2, tmY1, tmY2;  // stationary pair (A operands) and streamed pair (B operands)
+    const float* key_bias;               // [B, Sk] or null
+    const float* lse;                    // [B, H, Sq]
+    const float* delta;                  // [B, H, Sq]
+    __nv_bfloat16* out1;                 // DKV: dV [B,H,Sk,64]
+    __nv_bfloat16* out2;                 // DKV: dK [B,H,Sk,64];  !DKV: dQ [B,H,Sq,64]
+    int B, H, Sq, Sk;
+    float scale, scale_log2;
+};
+
+constexpr int BWD_Y_STAGES = 2;
+constexpr int BWD_SMEM = 2 * TILE_BYTES /*X1,X2*/ + BWD_Y_STAGES * 2 * TILE_BYTES /*Y1,Y2*/ + 4 * TILE_BYTES /*P, dS*/ +
+                         2 * 2 * TILE * 4 /*col vectors, double-buffered*/ + 1024 + 256;
+
+template <bool DKV>
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sX1 = smem;
+    uint8_t* sX2 = sX1 + TILE_BYTES;
+    uint8_t* sY = sX2 + TILE_BYTES;                       // stage s: Y1 at +s*32K, Y2 at +16K
+    uint8_t* sP = sY + BWD_Y_STAGES * 2 * TILE_BYTES;     // 2 chunks  (P^T, DKV only)
+    uint8_t* sDS = sP + 2 * TILE_BYTES;                   // 2 chunks
+    float* sColA = reinterpret_cast<float*>(sDS + 2 * TILE_BYTES);  // [2][128]
+    float* sColD = sColA + 2 * TILE;                                 // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sColD + 2 * TILE);
+    uint64_t* x_full = bars;
+    uint64_t* y_full = bars + 1;   // [2]
+    uint64_t* y_empty = bars + 3;  // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* ds_full = bars + 6;
+    uint64_t* mm_done = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x0 = blockIdx.x * TILE;
+    const int bh = blockIdx.y;
+    const int b = bh / p.H, h = bh % p.H;
+    const int rowsX = DKV ? p.Sk : p.Sq;
+    const int rowsY = DKV ? p.Sq : p.Sk;
+    const int n_y = (rowsY + TILE - 1) / TILE;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmX1);
+        tma_prefetch_desc(&p.tmX2);
+        tma_prefetch_desc(&p.tmY1);
+        tma_prefetch_desc(&p.tmY2);
+        mbar_init(x_full, 1);
+        for (int i = 0; i < BWD_Y_STAGES; ++i) {
+            mbar_init(&y_full[i], 1);
+            mbar_init(&y_empty[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(ds_full, 128);
+        mbar_init(mm_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS = tmem, tDP = tmem + 128, tO1 = tmem + 256, tO2 = tmem + 320;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(x_full, 2 * TILE_BYTES);
+            tma_load_4d(sX1, &p.tmX1, x_full, 0, h, x0, b);
+            tma_load_4d(sX2, &p.tmX2, x_full, 0, h, x0, b);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < n_y; ++i) {
+                mbar_wait(&y_empty[stage], phase ^ 1);
+                mbar_expect_tx(&y_full[stage], 2 * TILE_BYTES);
+                tma_load_4d(sY + stage * 2 * TILE_BYTES, &p.tmY1, &y_full[stage], 0, h, i * TILE, b);
+                tma_load_4d(sY + stage * 2 * TILE_BYTES + TILE_BYTES, &p.tmY2, &y_full[stage], 0, h, i * TILE, b);
+                if (++stage == BWD_Y_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+            mbar_wait(x_full, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t aX1 = smem_u32(sX1), aX2 = smem_u32(sX2), aP = smem_u32(sP), aDS = smem_u32(sDS);
+            for (int i = 0; i < n_y; ++i) {
+                mbar_wait(&y_full[stage], phase);
+                tc_fence_after();
+                const uint32_t aY1 = smem_u32(sY + stage * 2 * TILE_BYTES), aY2 = aY1 + TILE_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16(tS, make_sdesc_sw128(aX1 + k * 32, 16, 1024), make_sdesc_sw128(aY1 + k * 32, 16, 1024),
+                             idesc_s, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16(tDP, make_sdesc_sw128(aX2 + k * 32, 16, 1024), make_sdesc_sw128(aY2 + k * 32, 16, 1024),
+                             idesc_s, k > 0);
+                umma_commit(s_full);
+                mbar_wait(ds_full, i & 1);
+                tc_fence_after();
+                if (DKV) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)  // out1 (dV) += P^T . dO_i   (Y2 as MN-major B)
+                        umma_f16(tO1, make_sdesc_sw128(aP + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
+                                 make_sdesc_sw128(aY2 + k * 2048, 8192, 1024), idesc_o, (i > 0 || k > 0) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)  // out2 += dS . Y1   (Y1 as MN-major B)
+                    umma_f16(tO2, make_sdesc_sw128(aDS + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
+                             make_sdesc_sw128(aY1 + k * 2048, 8192, 1024), idesc_o, (i > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&y_empty[stage]);
+                umma_commit(mm_done);
+                if (++stage == BWD_Y_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int qd = warp & 3;
+        const int r = qd * 32 + lane;
+        const int tid128 = (warp - 2) * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const int xrow = x0 + r;
+        const bool row_ok = xrow < rowsX;
+        const long long bhoff = (long long)b * p.H + h;
+        // per-row scalars
+        float rowA, rowD = 0.f;
+        if (DKV) {
+            rowA = (p.key_bias && row_ok) ? p.key_bias[(long long)b * p.Sk + xrow] * LOG2E : 0.f;
+        } else {
+            rowA = row_ok ? -p.lse[bhoff * p.Sq + xrow] * LOG2E : 0.f;
+            rowD = row_ok ? p.delta[bhoff * p.Sq + xrow] : 0.f;
+        }
+        if (!row_ok) rowA = -INFINITY;
+        for (int i = 0; i < n_y; ++i) {
+            // column vectors of this streamed tile (double-buffered by parity)
+            float* cA = sColA + (i & 1) * TILE;
+            float* cD = sColD + (i & 1) * TILE;
+            {
+                const int ycol = i * TILE + tid128;
+                const bool ok = ycol < rowsY;
+                if (DKV) {
+                    cA[tid128] = ok ? -p.lse[bhoff * p.Sq + ycol] * LOG2E : -INFINITY;
+                    cD[tid128] = ok ? p.delta[bhoff * p.Sq + ycol] : 0.f;
+                } else {
+                    cA[tid128] = ok ? (p.key_bias ? p.key_bias[(long long)b * p.Sk + ycol] * LOG2E : 0.f) : -INFINITY;
+                    cD[tid128] = 0.f;
+                }
+            }
+            named_bar_sync(1, 128);
+            mbar_wait(s_full, i & 1);
+            tc_fence_after();
+            // P / dS smem buffers are free once the previous iteration's MMAs have completed
+            if (i > 0) {
+                mbar_wait(mm_done, (i - 1) & 1);
+                tc_fence_after();
+            }
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t sv[32], dv[32];
+                tmem_ld32(tS + lane_off + c * 32, sv);
+                tmem_ld32(tDP + lane_off + c * 32, dv);
+                tmem_ld_wait();
+                float pe[32], ds[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int cc = c * 32 + e;
+                    float x = __uint_as_float(sv[e]) * p.scale_log2 + rowA + cA[cc];
+                    float pp = fast_exp2(x);
+                    float dd = __uint_as_float(dv[e]) - (DKV ? cD[cc] : rowD);
+                    pe[e] = pp;
+                    ds[e] = pp * dd * p.scale;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t off = (uint32_t)((c >> 1) * TILE_BYTES) + sw128_off(r, (c & 1) * 4 + u);
+                    if (DKV) {
+                        uint4 w = make_uint4(pack_bf16x2(pe[u * 8], pe[u * 8 + 1]), pack_bf16x2(pe[u * 8 + 2], pe[u * 8 + 3]),
+                                             pack_bf16x2(pe[u * 8 + 4], pe[u * 8 + 5]), pack_bf16x2(pe[u * 8 + 6], pe[u * 8 + 7]));
+                        *reinterpret_cast<uint4*>(sP + off) = w;
+                    }
+                    uint4 w2 = make_uint4(pack_bf16x2(ds[u * 8], ds[u * 8 + 1]), pack_bf16x2(ds[u * 8 + 2], ds[u * 8 + 3]),
+                                          pack_bf16x2(ds[u * 8 + 4], ds[u * 8 + 5]), pack_bf16x2(ds[u * 8 + 6], ds[u * 8 + 7]));
+                    *reinterpret_cast<uint4*>(sDS + off) = w2;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(ds_full);
+        }
+        // ---- epilogue: accumulators -> [B,H,rowsX,64] bf16
+        mbar_wait(mm_done, (n_y - 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int which = DKV ? 0 : 1; which < 2; ++which) {
+            __nv_bfloat16* dst = (which == 0 ? p.out1 : p.out2) + (bhoff * rowsX + xrow) * HD;
+            const uint32_t tacc = which == 0 ? tO1 : tO2;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tacc + lane_off + c * 32, v);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 w = make_uint4(pack_bf16x2(__uint_as_float(v[u * 8]), __uint_as_float(v[u * 8 + 1])),
+                                             pack_bf16x2(__uint_as_float(v[u * 8 + 2]), __uint_as_float(v[u * 8 + 3])),
+                                             pack_bf16x2(__uint_as_float(v[u * 8 + 4]), __uint_as_float(v[u * 8 + 5])),
+                                             pack_bf16x2(__uint_as_float(v[u * 8 + 6]), __uint_as_float(v[u * 8 + 7])));
+                        *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = w;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// 4-D map over a head-split view: dims (innermost first) [64, H, S, B]; strides in elements.
+static int make_head_map(CUtensorMap* m, const void* base, int B, int H, int S, long long stride_h, long long stride_s,
+                         long long stride_b) {
+    uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)S, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)stride_h * 2, (uint64_t)stride_s * 2, (uint64_t)stride_b * 2};
+    uint32_t box[4] = {64, 1, 128, 1};
+    return make_tmap_nd(m, base, 4, dims, strides, box, 2, 1);
+}
+
+template <typename K>
+static int set_smem(K kern, int bytes, const char* name) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "cudaFuncSetAttribute(%s): %s", name, cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace b2d
+
+using namespace b2d;
+
+extern "C" int b2d_attn_fwd(const void* q, const void* k, const void* v, const float* key_bias, void* out, float* lse,
+                            int32_t B, int32_t H, int32_t Sq, int32_t Sk, float scale, void* stream) {
+    if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) return set_error(B2D_ERR_SHAPE, "attn_fwd: bad dims");
+    AttnFwdParams p;
+    memset(&p, 0, sizeof(p));
+    int rc;
+    if ((rc = make_head_map(&p.tmQ, q, B, H, Sq, (long long)Sq * 64, 64, (long long)H * Sq * 64))) return rc;
+    if ((rc = make_head_map(&p.tmK, k, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64))) return rc;
+    if ((rc = make_head_map(&p.tmV, v, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64))) return rc;
+    p.key_bias = key_bias;
+    p.out = (__nv_bfloat16*)out;
+    p.lse = lse;
+    p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
+    p.scale_log2 = scale * LOG2E;
+    if ((rc = set_smem(attn_fwd_kernel, FWD_SMEM, "attn_fwd"))) return rc;
+    dim3 grid((Sq + TILE - 1) / TILE, B * H);
+    attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    B2D_CHECK_LAUNCH("attn_fwd");
+    return 0;
+}
+
+extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const float* key_bias, const void* out,
+                            const void* dout, const float* lse, float* delta_ws, void* dq, void* dk, void* dv,
+                            int32_t B, int32_t H, int32_t Sq, int32_t Sk, float scale, void* stream) {
+    if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) return set_error(B2D_ERR_SHAPE, "attn_bwd: bad dims");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    {
+        long long total = (long long)B * Sq * H * 8;
+        attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)out,
+                                                                           (const __nv_bfloat16*)dout, delta_ws, B, H, Sq);
+        B2D_CHECK_LAUNCH("attn_delta");
+    }
+    CUtensorMap mQ, mK, mV, mdO;
+    int rc;
+    if ((rc = make_head_map(&mQ, q, B, H, Sq, (long long)Sq * 64, 64, (long long)H * Sq * 64))) return rc;
+    if ((rc = make_head_map(&mK, k, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64))) return rc;
+    if ((rc = make_head_map(&mV, v, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64))) return rc;
+    if ((rc = make_head_map(&mdO, dout, B, H, Sq, 64, (long long)H * 64, (long long)Sq * H * 64))) return rc;
+    AttnBwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.key_bias = key_bias; p.lse = lse; p.delta = delta_ws;
+    p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
+    p.scale = scale; p.scale_log2 = scale * LOG2E;
+    // dK, dV
+    p.tmX1 = mK; p.tmX2 = mV; p.tmY1 = mQ; p.tmY2 = mdO;
+    p.out1 = (__nv_bfloat16*)dv; p.out2 = (__nv_bfloat16*)dk;
+    if ((rc = set_smem(attn_bwd_kernel<true>, BWD_SMEM, "attn_bwd_dkv"))) return rc;
+    attn_bwd_kernel<true><<<dim3((Sk + TILE - 1) / TILE, B * H), ATT_THREADS, BWD_SMEM, st>>>(p);
+    B2D_CHECK_LAUNCH("attn_bwd_dkv");
+    // dQ
+    p.tmX1 = mQ; p.tmX2 = mdO; p.tmY1 = mK; p.tmY2 = mV;
+    p.out1 = nullptr; p.out2 = (__nv_bfloat16*)dq;
+    if ((rc = set_smem(attn_bwd_kernel<false>, BWD_SMEM, "attn_bwd_dq"))) return rc;
+    attn_bwd_kernel<false><<<dim3((Sq + TILE - 1) / TILE, B * H), ATT_THREADS, BWD_SMEM, st>>>(p);
+    B2D_CHECK_LAUNCH("attn_bwd_dq");
+    return 0;
+}

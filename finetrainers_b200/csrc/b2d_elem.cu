@@ -1,0 +1,644 @@
+// b2d_elem.cu — the HBM-bound satellites of the DiT step: fused norm+AdaLN modulate (fwd/bwd), q/k RMSNorm + RoPE +
+// head split (fwd/bwd), RoPE table, noise/pack prologue, MSE loss + dpred, sinusoid, casts, flat clip + AdamW.
+// All: 128-bit coalesced global access, fp32 math, warp-shuffle reductions; one row per CTA of 256 threads.
+#include "b2d_internal.h"
+#include "b2d_ptx.cuh"
+
+namespace b2d {
+
+constexpr int ROW_THREADS = 256;
+constexpr int MAX_CHUNKS = 4;  // D <= 8 * 256 * 4 = 8192
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void stg16(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+
+__device__ __forceinline__ void unpack8(uint4 u, float (&f)[8]) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// block-wide sum of up to two values; all threads get the result
+__device__ __forceinline__ float2 block_sum2(float a, float b) {
+    __shared__ float sa[ROW_THREADS / 32], sb[ROW_THREADS / 32];
+    __shared__ float ra, rb;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();  // protect sa/sb/ra/rb reuse across consecutive calls
+    if (l == 0) { sa[w] = a; sb[w] = b; }
+    __syncthreads();
+    if (w == 0) {
+        float x = l < ROW_THREADS / 32 ? sa[l] : 0.f;
+        float y = l < ROW_THREADS / 32 ? sb[l] : 0.f;
+        x = warp_sum(x);
+        y = warp_sum(y);
+        if (l == 0) { ra = x; rb = y; }
+    }
+    __syncthreads();
+    return make_float2(ra, rb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// norm + modulate
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) norm_modulate_fwd_kernel(
+    const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ shift_tab,
+    const __nv_bfloat16* __restrict__ shift_emb, const __nv_bfloat16* __restrict__ scale_tab,
+    const __nv_bfloat16* __restrict__ scale_emb, long long emb_stride, int D, int rows_per_sample, float eps,
+    int layer_norm) {
+    const int row = blockIdx.x;
+    const int b = row / rows_per_sample;
+    const __nv_bfloat16* xr = x + (long long)row * D;
+    float v[MAX_CHUNKS][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAX_CHUNKS; ++c) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            unpack8(ldg16(xr + col), v[c]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s1 += v[c][e]; s2 += v[c][e] * v[c][e]; }
+        }
+    }
+    float2 tot = block_sum2(s1, s2);
+    float mean = 0.f, rstd;
+    if (layer_norm) {
+        mean = tot.x / D;
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAX_CHUNKS; ++c) {
+            const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+            if (col < D) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { float d = v[c][e] - mean; var += d * d; }
+            }
+        }
+        float2 t2 = block_sum2(var, 0.f);
+        rstd = rsqrtf(t2.x / D + eps);
+    } else {
+        rstd = rsqrtf(tot.y / D + eps);
+    }
+#pragma unroll
+    for (int c = 0; c < MAX_CHUNKS; ++c) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            float sh[8], sc[8], t[8];
+            unpack8(ldg16(shift_tab + col), sh);
+            unpack8(ldg16(shift_emb + (long long)b * emb_stride + col), t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sh[e] += t[e];
+            unpack8(ldg16(scale_tab + col), sc);
+            unpack8(ldg16(scale_emb + (long long)b * emb_stride + col), t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sc[e] += t[e];
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (v[c][e] - mean) * rstd * (1.f + sc[e]) + sh[e];
+            stg16(y + (long long)row * D + col, pack8(o));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
+    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dx_in,
+    __nv_bfloat16* __restrict__ dx_out, const __nv_bfloat16* __restrict__ scale_tab,
+    const __nv_bfloat16* __restrict__ scale_emb, const __nv_bfloat16* __restrict__ gate2_tab,
+    const __nv_bfloat16* __restrict__ gate2_emb, __nv_bfloat16* __restrict__ out2, long long emb_stride, int D,
+    int rows_per_sample, float eps, int layer_norm) {
+    const int row = blockIdx.x;
+    const int b = row / rows_per_sample;
+    const long long ro = (long long)row * D;
+    float xv[MAX_CHUNKS][8], g[MAX_CHUNKS][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAX_CHUNKS; ++c) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            unpack8(ldg16(x + ro + col), xv[c]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s1 += xv[c][e]; s2 += xv[c][e] * xv[c][e]; }
+        }
+    }
+    float2 tot = block_sum2(s1, s2);
+    float mean = 0.f, rstd;
+    if (layer_norm) {
+        mean = tot.x / D;
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAX_CHUNKS; ++c) {
+            const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+            if (col < D) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { float d = xv[c][e] - mean; var += d * d; }
+            }
+        }
+        rstd = rsqrtf(block_sum2(var, 0.f).x / D + eps);
+    } else {
+        rstd = rsqrtf(tot.y / D + eps);
+    }
+    // g = dy * (1 + scale);  xhat = (x - mean) * rstd;  a = sum(g), c = sum(g * xhat)
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAX_CHUNKS; ++c) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            float sc[8], t[8], d[8];
+            unpack8(ldg16(scale_tab + col), sc);
+            unpack8(ldg16(scale_emb + (long long)b * emb_stride + col), t);
+            unpack8(ldg16(dy + ro + col), d);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                g[c][e] = d[e] * (1.f + sc[e] + t[e]);
+                xv[c][e] = (xv[c][e] - mean) * rstd;
+                sg += g[c][e];
+                sgx += g[c][e] * xv[c][e];
+            }
+        }
+    }
+    float2 t2 = block_sum2(sg, sgx);
+    const float mg = layer_norm ? t2.x / D : 0.f;
+    const float mgx = t2.y / D;
+#pragma unroll
+    for (int c = 0; c < MAX_CHUNKS; ++c) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            float o[8];
+            if (dx_in != nullptr) unpack8(ldg16(dx_in + ro + col), o);
+            else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] += rstd * (g[c][e] - mg - xv[c][e] * mgx);
+            uint4 packed = pack8(o);
+            stg16(dx_out + ro + col, packed);
+            if (out2 != nullptr) {
+                float r[8], gt[8], ge[8];
+                unpack8(packed, r);  // the rounded value is what downstream sees
+                unpack8(ldg16(gate2_tab + col), gt);
+                unpack8(ldg16(gate2_emb + (long long)b * emb_stride + col), ge);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) r[e] *= (gt[e] + ge[e]);
+                stg16(out2 + ro + col, pack8(r));
+            }
+        }
+    }
+}
+
+__global__ void colscale_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                const __nv_bfloat16* __restrict__ tab, const __nv_bfloat16* __restrict__ emb,
+                                long long emb_stride, long long total8, int D, int rows_per_sample) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total8) return;
+    long long e0 = i * 8;
+    int row = (int)(e0 / D);
+    int col = (int)(e0 % D);
+    int b = row / rows_per_sample;
+    float v[8], t[8], g[8];
+    unpack8(ldg16(x + e0), v);
+    unpack8(ldg16(tab + col), t);
+    unpack8(ldg16(emb + (long long)b * emb_stride + col), g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= (t[e] + g[e]);
+    stg16(out + e0, pack8(v));
+}
+
+// ------------------------------------------------------------------------------------------------
+// q/k RMSNorm (affine, across all heads) + RoPE + head split:  src[row, col_off + c] -> dst[b, h, s, d]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) qknorm_rope_fwd_kernel(
+    const __nv_bfloat16* __restrict__ src, long long ld, long long col_off, const __nv_bfloat16* __restrict__ weight,
+    const float* __restrict__ cosT, const float* __restrict__ sinT, __nv_bfloat16* __restrict__ dst, int S, int H,
+    int norm, float eps) {
+    const int D = H * 64;
+    const int row = blockIdx.x;
+    const int b = row / S, s = row % S;
+    const __nv_bfloat16* xr = src + (long long)row * ld + col_off;
+    float v[MAX_CHUNKS][8];
+    float s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAX_CHUNKS; ++c) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            unpack8(ldg16(xr + col), v[c]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s2 += v[c][e] * v[c][e];
+        }
+    }
+    float rstd = 1.f;
+    if (norm) rstd = rsqrtf(block_sum2(s2, 0.f).x / D + eps);
+#pragma unroll
+    for (int c = 0; c < MAX_CHUNKS; ++c) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            float n[8];
+            if (norm) {
+                float w[8];
+                unpack8(ldg16(weight + col), w);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) n[e] = v[c][e] * rstd * w[e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) n[e] = v[c][e];
+            }
+            float o[8];
+            if (cosT != nullptr) {
+                const float4* cp = reinterpret_cast<const float4*>(cosT + (long long)s * D + col);
+                const float4* sp = reinterpret_cast<const float4*>(sinT + (long long)s * D + col);
+                float4 c0 = cp[0], c1 = cp[1], s0 = sp[0], s1 = sp[1];
+                const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                    o[e] = n[e] * cs[e] - n[e + 1] * sn[e];
+                    o[e + 1] = n[e + 1] * cs[e + 1] + n[e] * sn[e + 1];
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = n[e];
+            }
+            const int h = col >> 6, d = col & 63;
+            stg16(dst + (((long long)b * H + h) * S + s) * 64 + d, pack8(o));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) qknorm_rope_bwd_kernel(
+    const __nv_bfloat16* __restrict__ dyh, const __nv_bfloat16* __restrict__ x, long long ld, long long col_off,
+    const __nv_bfloat16* __restrict__ weight, const float* __restrict__ cosT, const float* __restrict__ sinT,
+    __nv_bfloat16* __restrict__ dx, long long ld_dx, long long dx_col_off, int S, int H, int norm, float eps) {
+    const int D = H * 64;
+    const int row = blockIdx.x;
+    const int b = row / S, s = row % S;
+    float xv[MAX_CHUNKS][8], g[MAX_CHUNKS][8];
+    float s2 = 0.f;
+    if (norm) {
+        const __nv_bfloat16* xr = x + (long long)row * ld + col_off;
+#pragma unroll
+        for (int c = 0; c < MAX_CHUNKS; ++c) {
+            const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+            if (col < D) {
+                unpack8(ldg16(xr + col), xv[c]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s2 += xv[c][e] * xv[c][e];
+            }
+        }
+    }
+    float rstd = 1.f;
+    if (norm) rstd = rsqrtf(block_sum2(s2, 0.f).x / D + eps);
+    float sgx = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAX_CHUNKS; ++c) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            const int h = col >> 6, d = col & 63;
+            float dy[8], dn[8];
+            unpack8(ldg16(dyh + (((long long)b * H + h) * S + s) * 64 + d), dy);
+            if (cosT != nullptr) {
+                const float4* cp = reinterpret_cast<const float4*>(cosT + (long long)s * D + col);
+                const float4* sp = reinterpret_cast<const float4*>(sinT + (long long)s * D + col);
+                float4 c0 = cp[0], c1 = cp[1], s0 = sp[0], s1 = sp[1];
+                const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                    dn[e] = dy[e] * cs[e] + dy[e + 1] * sn[e + 1];
+                    dn[e + 1] = dy[e + 1] * cs[e + 1] - dy[e] * sn[e];
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dn[e] = dy[e];
+            }
+            if (norm) {
+                float w[8];
+                unpack8(ldg16(weight + col), w);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    g[c][e] = dn[e] * w[e];
+                    xv[c][e] *= rstd;
+                    sgx += g[c][e] * xv[c][e];
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) g[c][e] = dn[e];
+            }
+        }
+    }
+    float mgx = 0.f;
+    if (norm) mgx = block_sum2(sgx, 0.f).x / D;
+#pragma unroll
+    for (int c = 0; c < MAX_CHUNKS; ++c) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = norm ? rstd * (g[c][e] - xv[c][e] * mgx) : g[c][e];
+            stg16(dx + (long long)row * ld_dx + dx_col_off + col, pack8(o));
+        }
+    }
+}
+
+// RoPE table: diffusers LTXVideoRotaryPosEmbed, fp32.  One thread per (s, pair).
+__global__ void rope_table_kernel(float* __restrict__ cosT, float* __restrict__ sinT, int F, int H, int W, int D,
+                                  float sf, float sh, float sw) {
+    const int nf = D / 6;
+    const int pad = D % 6;
+    const long long S = (long long)F * H * W;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pairs = D / 2;
+    if (idx >= S * pairs) return;
+    const int s = (int)(idx / pairs);
+    const int pr = (int)(idx % pairs);
+    const int col = pr * 2;
+    float c = 1.f, sn = 0.f;
+    if (col >= pad) {
+        const int j = (col - pad) / 2;
+        const int fi = j / 3, axis = j % 3;
+        const int w = s % W, h = (s / W) % H, f = s / (W * H);
+        float g = axis == 0 ? (float)f * sf : (axis == 1 ? (float)h * sh : (float)w * sw);
+        // torch.linspace(0, 1, nf) (symmetric evaluation), theta ** x, * pi/2, * (2g - 1): same op order, fp32
+        const float step = 1.0f / (float)(nf - 1);
+        float lin = (fi < nf / 2) ? (float)fi * step : 1.0f - (float)(nf - 1 - fi) * step;
+        float fr = powf(10000.0f, lin);
+        fr = fr * 1.5707963267948966f;
+        float ang = fr * (g * 2.0f - 1.0f);
+        c = cosf(ang);
+        sn = sinf(ang);
+    }
+    cosT[(long long)s * D + col] = c;
+    cosT[(long long)s * D + col + 1] = c;
+    sinT[(long long)s * D + col] = sn;
+    sinT[(long long)s * D + col + 1] = sn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// step prologue: normalise + flow-match x_t + pack [B,C,F,HW] -> [B, F*HW, C]; target = n - x0.
+// Rounding points mirror the reference's bf16 tensors (base_specification.py:295-322): x0 rounded to bf16, x_t computed
+// in fp32 from (bf16 x0, bf16 n, fp32 sigma) then rounded, target = bf16(n - x0).
+// ------------------------------------------------------------------------------------------------
+__global__ void prep_noise_pack_kernel(const __nv_bfloat16* __restrict__ lat, const __nv_bfloat16* __restrict__ noise,
+                                       const float* __restrict__ mean, const float* __restrict__ stdv,
+                                       const float* __restrict__ sigma, const float* __restrict__ sigma_ff,
+                                       __nv_bfloat16* __restrict__ x_t, __nv_bfloat16* __restrict__ target, int B,
+                                       int C, int F, int HW) {
+    const long long S = (long long)F * HW;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * S * C) return;
+    const int c = (int)(idx % C);
+    const long long s = (idx / C) % S;
+    const int b = (int)(idx / (C * S));
+    const long long src = ((long long)b * C + c) * S + s;
+    float x = __bfloat162float(lat[src]);
+    float x0f = __fdiv_rn(__fmul_rn(__fsub_rn(x, mean[b * C + c]), 1.0f), stdv[b * C + c]);
+    float x0 = __bfloat162float(__float2bfloat16_rn(x0f));
+    float n = __bfloat162float(noise[src]);
+    float sg = sigma[b];
+    if (sigma_ff != nullptr && s < HW) sg = sigma_ff[b];
+    float xt = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, sg), x0), __fmul_rn(sg, n));
+    x_t[idx] = __float2bfloat16_rn(xt);
+    target[idx] = __float2bfloat16_rn(__fsub_rn(n, x0));
+}
+
+// ------------------------------------------------------------------------------------------------
+// loss = mean_b( mean_i( w_b (p - t)^2 ) ) * loss_scale ; dpred = 2 w_b (p - t) / (n B) * loss_scale
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) loss_mse_kernel(const __nv_bfloat16* __restrict__ pred,
+                                                               const __nv_bfloat16* __restrict__ target,
+                                                               const float* __restrict__ weight, float loss_scale,
+                                                               __nv_bfloat16* __restrict__ dpred,
+                                                               float* __restrict__ partial, int B,
+                                                               long long per_sample) {
+    const long long total8 = (long long)B * per_sample / 8;
+    float acc = 0.f;
+    const float inv = loss_scale / ((float)per_sample * (float)B);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+        const long long e0 = i * 8;
+        const int b = (int)(e0 / per_sample);
+        const float w = weight ? weight[b] : 1.f;
+        float p[8], t[8], g[8];
+        unpack8(ldg16(pred + e0), p);
+        unpack8(ldg16(target + e0), t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float d = p[e] - t[e];
+            acc += w * d * d;
+            g[e] = 2.f * w * d * inv;
+        }
+        if (dpred) stg16(dpred + e0, pack8(g));
+    }
+    float2 r = block_sum2(acc, 0.f);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r.x * inv;
+}
+__global__ void final_sum_kernel(const float* __restrict__ partial, int n, float* __restrict__ out, int accumulate) {
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a += partial[i];
+    float2 r = block_sum2(a, 0.f);
+    if (threadIdx.x == 0) *out = accumulate ? (*out + r.x) : r.x;
+}
+
+__global__ void timestep_sinusoid_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int n) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * 128) return;
+    const int i = idx % 128, r = idx / 128;
+    const float freq = expf(-9.210340371976184f * (float)i / 128.0f);
+    const float a = t[r] * freq;
+    out[(long long)r * 256 + i] = __float2bfloat16_rn(cosf(a));
+    out[(long long)r * 256 + 128 + i] = __float2bfloat16_rn(sinf(a));
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n,
+                                     float scale) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        float4 v = *reinterpret_cast<const float4*>(src + i);
+        uint2 o = make_uint2(pack_bf16x2(v.x * scale, v.y * scale), pack_bf16x2(v.z * scale, v.w * scale));
+        *reinterpret_cast<uint2*>(dst + i) = o;
+    } else {
+        for (; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i] * scale);
+    }
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) sumsq_kernel(const float* __restrict__ x, long long n,
+                                                            float* __restrict__ partial) {
+    float acc = 0.f;
+    const long long n4 = n / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(x)[i];
+        acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (long long i = n4 * 4; i < n; ++i) acc += x[i] * x[i];
+    float2 r = block_sum2(acc, 0.f);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r.x;
+}
+
+// clip (utils/torch.py:99-161: coef = min(1, max_norm / (norm + 1e-6))) + AdamW (torch.optim.AdamW math) + zero grad
+__global__ void adamw_clip_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                  float* __restrict__ v, long long n, const float* __restrict__ sumsq, float max_norm,
+                                  float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                                  float grad_div) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float coef = grad_div;
+    if (max_norm > 0.f) {
+        float norm = sqrtf(*sumsq) * grad_div;
+        coef *= fminf(1.f, max_norm / (norm + 1e-6f));
+    }
+    float gi = g[i] * coef;
+    float pi = p[i];
+    pi *= (1.f - lr * wd);
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi;
+    m[i] = mi;
+    v[i] = vi;
+    g[i] = 0.f;
+}
+
+}  // namespace b2d
+
+using namespace b2d;
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+
+static int check_rowop(int rows, int D, int rps) {
+    if (rows <= 0 || D <= 0 || rps <= 0) return set_error(B2D_ERR_SHAPE, "rows/D/rows_per_sample must be positive");
+    if (D % 8 != 0 || D > 8 * ROW_THREADS * MAX_CHUNKS) return set_error(B2D_ERR_SHAPE, "D=%d must be a multiple of 8 and <= %d", D, 8 * ROW_THREADS * MAX_CHUNKS);
+    return 0;
+}
+
+extern "C" int b2d_norm_modulate_fwd(const void* x, void* y, const void* shift_tab, const void* shift_emb,
+                                     const void* scale_tab, const void* scale_emb, int64_t emb_stride, int32_t rows,
+                                     int32_t D, int32_t rows_per_sample, float eps, int32_t layer_norm, void* stream) {
+    if (int rc = check_rowop(rows, D, rows_per_sample)) return rc;
+    norm_modulate_fwd_kernel<<<rows, ROW_THREADS, 0, STREAM>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)shift_tab, (const __nv_bfloat16*)shift_emb,
+        (const __nv_bfloat16*)scale_tab, (const __nv_bfloat16*)scale_emb, emb_stride, D, rows_per_sample, eps, layer_norm);
+    B2D_CHECK_LAUNCH("norm_modulate_fwd");
+    return 0;
+}
+
+extern "C" int b2d_norm_modulate_bwd(const void* dy, const void* x, const void* dx_in, void* dx_out,
+                                     const void* scale_tab, const void* scale_emb, const void* gate2_tab,
+                                     const void* gate2_emb, void* out2, int64_t emb_stride, int32_t rows, int32_t D,
+                                     int32_t rows_per_sample, float eps, int32_t layer_norm, void* stream) {
+    if (int rc = check_rowop(rows, D, rows_per_sample)) return rc;
+    norm_modulate_bwd_kernel<<<rows, ROW_THREADS, 0, STREAM>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dx_in, (__nv_bfloat16*)dx_out,
+        (const __nv_bfloat16*)scale_tab, (const __nv_bfloat16*)scale_emb, (const __nv_bfloat16*)gate2_tab,
+        (const __nv_bfloat16*)gate2_emb, (__nv_bfloat16*)out2, emb_stride, D, rows_per_sample, eps, layer_norm);
+    B2D_CHECK_LAUNCH("norm_modulate_bwd");
+    return 0;
+}
+
+extern "C" int b2d_colscale(const void* x, void* out, const void* tab, const void* emb, int64_t emb_stride,
+                            int32_t rows, int32_t D, int32_t rows_per_sample, void* stream) {
+    if (D % 8) return set_error(B2D_ERR_SHAPE, "colscale: D %% 8");
+    long long total8 = (long long)rows * D / 8;
+    colscale_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, STREAM>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out,
+                                                                          (const __nv_bfloat16*)tab,
+                                                                          (const __nv_bfloat16*)emb, emb_stride, total8,
+                                                                          D, rows_per_sample);
+    B2D_CHECK_LAUNCH("colscale");
+    return 0;
+}
+
+extern "C" int b2d_qknorm_rope_fwd(const void* src, int64_t ld, int64_t col_off, const void* weight, const void* cos,
+                                   const void* sin, void* dst, int32_t B, int32_t S, int32_t H, int32_t norm,
+                                   float eps, void* stream) {
+    if (int rc = check_rowop(B * S, H * 64, S)) return rc;
+    if ((ld % 8) || (col_off % 8)) return set_error(B2D_ERR_ALIGN, "qknorm_rope: ld/col_off must be multiples of 8");
+    qknorm_rope_fwd_kernel<<<B * S, ROW_THREADS, 0, STREAM>>>((const __nv_bfloat16*)src, ld, col_off,
+                                                              (const __nv_bfloat16*)weight, (const float*)cos,
+                                                              (const float*)sin, (__nv_bfloat16*)dst, S, H, norm, eps);
+    B2D_CHECK_LAUNCH("qknorm_rope_fwd");
+    return 0;
+}
+
+extern "C" int b2d_qknorm_rope_bwd(const void* dsrc_heads, const void* x, int64_t ld, int64_t col_off,
+                                   const void* weight, const void* cos, const void* sin, void* dx, int64_t ld_dx,
+                                   int64_t dx_col_off, int32_t B, int32_t S, int32_t H, int32_t norm, float eps,
+                                   void* stream) {
+    if (int rc = check_rowop(B * S, H * 64, S)) return rc;
+    if ((ld % 8) || (col_off % 8) || (ld_dx % 8) || (dx_col_off % 8))
+        return set_error(B2D_ERR_ALIGN, "qknorm_rope_bwd: ld/col_off must be multiples of 8");
+    qknorm_rope_bwd_kernel<<<B * S, ROW_THREADS, 0, STREAM>>>(
+        (const __nv_bfloat16*)dsrc_heads, (const __nv_bfloat16*)x, ld, col_off, (const __nv_bfloat16*)weight,
+        (const float*)cos, (const float*)sin, (__nv_bfloat16*)dx, ld_dx, dx_col_off, S, H, norm, eps);
+    B2D_CHECK_LAUNCH("qknorm_rope_bwd");
+    return 0;
+}
+
+extern "C" int b2d_rope_table(float* cos, float* sin, int32_t F, int32_t H, int32_t W, int32_t D, float sf, float sh,
+                              float sw, void* stream) {
+    if (D % 2 || D / 6 < 2) return set_error(B2D_ERR_SHAPE, "rope_table: D must be even and >= 12");
+    long long n = (long long)F * H * W * (D / 2);
+    rope_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(cos, sin, F, H, W, D, sf, sh, sw);
+    B2D_CHECK_LAUNCH("rope_table");
+    return 0;
+}
+
+extern "C" int b2d_prep_noise_pack(const void* latents, const void* noise, const float* mean, const float* std,
+                                   const float* sigma, const float* sigma_ff, void* x_t, void* target, int32_t B,
+                                   int32_t C, int32_t F, int32_t HW, void* stream) {
+    long long n = (long long)B * C * F * HW;
+    if (n <= 0) return set_error(B2D_ERR_SHAPE, "prep: empty");
+    prep_noise_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(
+        (const __nv_bfloat16*)latents, (const __nv_bfloat16*)noise, mean, std, sigma, sigma_ff, (__nv_bfloat16*)x_t,
+        (__nv_bfloat16*)target, B, C, F, HW);
+    B2D_CHECK_LAUNCH("prep_noise_pack");
+    return 0;
+}
+
+constexpr int REDUCE_BLOCKS = 296;
+
+extern "C" int b2d_loss_mse(const void* pred, const void* target, const float* weight, float loss_scale,
+                            float* loss_out, void* dpred, float* partial_ws, int32_t B, int64_t per_sample,
+                            void* stream) {
+    if (per_sample % 8) return set_error(B2D_ERR_SHAPE, "loss: per_sample %% 8");
+    loss_mse_kernel<<<REDUCE_BLOCKS, ROW_THREADS, 0, STREAM>>>((const __nv_bfloat16*)pred, (const __nv_bfloat16*)target,
+                                                               weight, loss_scale, (__nv_bfloat16*)dpred, partial_ws, B,
+                                                               per_sample);
+    B2D_CHECK_LAUNCH("loss_mse");
+    final_sum_kernel<<<1, ROW_THREADS, 0, STREAM>>>(partial_ws, REDUCE_BLOCKS, loss_out, 0);
+    B2D_CHECK_LAUNCH("loss_final");
+    return 0;
+}
+
+extern "C" int b2d_timestep_sinusoid(const float* t, void* out, int32_t n, void* stream) {
+    timestep_sinusoid_kernel<<<(n * 128 + 255) / 256, 256, 0, STREAM>>>(t, (__nv_bfloat16*)out, n);
+    B2D_CHECK_LAUNCH("timestep_sinusoid");
+    return 0;
+}
+
+extern "C" int b2d_cast_f32_bf16(const float* src, void* dst, int64_t n, float scale, void* stream) {
+    if (n <= 0) return 0;
+    long long n4 = (n + 3) / 4;
+    cast_f32_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, STREAM>>>(src, (__nv_bfloat16*)dst, n, scale);
+    B2D_CHECK_LAUNCH("cast_f32_bf16");
+    return 0;
+}
+
+extern "C" int b2d_sumsq(const float* x, int64_t n, float* out_sumsq, float* partial_ws, void* stream) {
+    sumsq_kernel<<<REDUCE_BLOCKS, ROW_THREADS, 0, STREAM>>>(x, n, partial_ws);
+    B2D_CHECK_LAUNCH("sumsq");
+    final_sum_kernel<<<1, ROW_THREADS, 0, STREAM>>>(partial_ws, REDUCE_BLOCKS, out_sumsq, 1);
+    B2D_CHECK_LAUNCH("sumsq_final");
+    return 0;
+}
+
+extern "C" int b2d_adamw_clip(float* p, float* g, float* m, float* v, int64_t n, const float* sumsq, float max_norm,
+                              float lr, float beta1, float beta2, float eps, float wd, int32_t step, float grad_div,
+                              void* stream) {
+    if (n <= 0) return 0;
+    float bc1 = 1.f - powf(beta1, (float)step);
+    float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+    adamw_clip_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(p, g, m, v, n, sumsq, max_norm, lr, beta1, beta2,
+                                                                        eps, wd, bc1, bc2s, grad_div);
+    B2D_CHECK_LAUNCH("adamw_clip");
+    return 0;
+}

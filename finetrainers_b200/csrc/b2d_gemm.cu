@@ -1,0 +1,536 @@
+// b2d_gemm.cu — persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   warp 0      : TMA producer (one elected lane)     global -> 128B-swizzled smem ring (mbarrier full/empty)
+//   warp 1      : MMA issuer (one elected lane) + TMEM owner; tcgen05.mma 128 x BLOCK_N x 16, fp32 accumulators in TMEM,
+//                 double-buffered so the epilogue of tile i overlaps the main loop of tile i+1
+//   warps 2..5  : epilogue; tcgen05.ld (one accumulator row per thread) -> fused epilogue -> global
+//
+// Operands may be K-major or MN-major (transposed views of row-major activations/weights), which covers
+// forward (x W^T), backward-dX (dY W) and backward-dW (dY^T X) without materialising transposes.
+// An optional second operand pair extends the contraction (LoRA: [x | u] [W | B]^T in one accumulator).
+#include "b2d_internal.h"
+#include "b2d_ptx.cuh"
+
+namespace b2d {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int GEMM_THREADS = 192;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+
+struct GemmKParams {
+    CUtensorMap tmA, tmB, tmA2, tmB2;
+    int M, N, K, K2;
+    int a2_group_n;
+    int splits, batch;
+    int a_brow, a_bcol, b_brow, b_bcol;
+    long long c_boff;
+    int epi;
+    float alpha;
+    void* out;
+    long long ldc;
+    void* out2;
+    long long ldc2;
+    const __nv_bfloat16* bias;
+    const __nv_bfloat16* res;
+    long long ldres;
+    const __nv_bfloat16* aux;
+    long long ldaux;
+    const __nv_bfloat16* gate_table;
+    const __nv_bfloat16* gate_temb;
+    const __nv_bfloat16* gate2_table;
+    const __nv_bfloat16* gate2_temb;
+    long long temb_stride;
+    int rows_per_sample;
+    int m_tiles, n_tiles, kb_main, kb_ext, total_work;
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = (220 * 1024 / STAGE_BYTES) > 8 ? 8 : (220 * 1024 / STAGE_BYTES);
+    static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void st_global_16B(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_global_16B(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmKParams p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + Cfg::STAGES;
+    uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+        if (p.K2 > 0) {
+            tma_prefetch_desc(&p.tmA2);
+            tma_prefetch_desc(&p.tmB2);
+        }
+        for (int i = 0; i < Cfg::STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int kb_total = p.kb_main + p.kb_ext;  // per work item when splits == 1
+    const int kb_per_split = (p.kb_main + p.splits - 1) / p.splits;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+                int mt = w % p.m_tiles;
+                int t = w / p.m_tiles;
+                int nt = t % p.n_tiles;
+                t /= p.n_tiles;
+                int sp = t % p.splits;
+                int z = t / p.splits;
+                const int m0 = mt * BLOCK_M, n0 = nt * BN;
+                int kb_begin = sp * kb_per_split;
+                int kb_end = min(p.kb_main, kb_begin + kb_per_split);
+                int n_ext = (sp == 0) ? p.kb_ext : 0;
+                int nkb = (kb_end - kb_begin) + n_ext;
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sB = sA + A_STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    const bool ext = i >= (kb_end - kb_begin);
+                    if (!ext) {
+                        const int k0 = (kb_begin + i) * BLOCK_K;
+                        if (A_MN == 0) {
+                            tma_load_2d(sA, &p.tmA, &full_bar[stage], k0 + z * p.a_bcol, m0 + z * p.a_brow);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BLOCK_M / 64; ++j)
+                                tma_load_2d(sA + j * 8192, &p.tmA, &full_bar[stage], m0 + 64 * j + z * p.a_bcol,
+                                            k0 + z * p.a_brow);
+                        }
+                        if (B_MN == 0) {
+                            tma_load_2d(sB, &p.tmB, &full_bar[stage], k0 + z * p.b_bcol, n0 + z * p.b_brow);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j)
+                                tma_load_2d(sB + j * 8192, &p.tmB, &full_bar[stage], n0 + 64 * j + z * p.b_bcol,
+                                            k0 + z * p.b_brow);
+                        }
+                    } else {
+                        const int k2 = (i - (kb_end - kb_begin)) * BLOCK_K;
+                        const int a2off = p.a2_group_n > 0 ? (n0 / p.a2_group_n) * p.K2 : 0;
+                        // A2 is always K-major [M, *]; B2 follows B's majorness
+                        tma_load_2d(sA, &p.tmA2, &full_bar[stage], k2 + a2off, m0);
+                        if (B_MN == 0) {
+                            tma_load_2d(sB, &p.tmB2, &full_bar[stage], k2, n0);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j)
+                                tma_load_2d(sB + j * 8192, &p.tmB2, &full_bar[stage], n0 + 64 * j, k2);
+                        }
+                    }
+                    if (++stage == Cfg::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (elect_one()) {
+            constexpr uint32_t idesc_main = make_idesc_bf16(BLOCK_M, BN, A_MN, B_MN);
+            constexpr uint32_t idesc_ext = make_idesc_bf16(BLOCK_M, BN, 0, B_MN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+                int t = w / p.m_tiles / p.n_tiles;
+                int sp = t % p.splits;
+                int kb_begin = sp * kb_per_split;
+                int kb_end = min(p.kb_main, kb_begin + kb_per_split);
+                int n_main = kb_end - kb_begin;
+                int nkb = n_main + ((sp == 0) ? p.kb_ext : 0);
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sB = sA + A_STAGE_BYTES;
+                    const bool ext = i >= n_main;
+                    const bool a_mn = (A_MN != 0) && !ext;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                        // K-major: +32 B per 16 K elements inside the 128 B swizzle row.
+                        // MN-major: +16 K-rows * 128 B.
+                        uint64_t ad = a_mn ? make_sdesc_sw128(sA + k * 2048, 8192, 1024)
+                                           : make_sdesc_sw128(sA + k * 32, 16, 1024);
+                        uint64_t bd = (B_MN != 0) ? make_sdesc_sw128(sB + k * 2048, 8192, 1024)
+                                                  : make_sdesc_sw128(sB + k * 32, 16, 1024);
+                        umma_f16(tmem_d, ad, bd, ext ? idesc_ext : idesc_main, (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == Cfg::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull_bar[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ============================== epilogue warps ==============================
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+            int mt = w % p.m_tiles;
+            int t = w / p.m_tiles;
+            int nt = t % p.n_tiles;
+            t /= p.n_tiles;
+            int z = t / p.splits;
+            const int row = mt * BLOCK_M + q * 32 + lane;
+            const int n0 = nt * BN;
+            const bool row_ok = row < p.M;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+            const int b = (p.rows_per_sample > 0) ? (row_ok ? row / p.rows_per_sample : 0) : 0;
+            const long long cbase = (long long)z * p.c_boff;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c * 32, r);
+                tmem_ld_wait();
+                const int col0 = n0 + c * 32;
+                if (row_ok && col0 < p.N) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+                    const int epi = p.epi;
+                    if (epi == B2D_EPI_F32_ATOMIC) {
+                        float* o = reinterpret_cast<float*>(p.out) + cbase + (long long)row * p.ldc + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N) atomicAdd(o + j, v[j]);
+                    } else if (epi == B2D_EPI_F32_ATOMIC_T) {
+                        float* o = reinterpret_cast<float*>(p.out) + cbase + row;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N) atomicAdd(o + (long long)(col0 + j) * p.ldc, v[j]);
+                    } else {
+                        if (p.bias != nullptr) {
+#pragma unroll
+                            for (int j8 = 0; j8 < 4; ++j8) {
+                                if (col0 + j8 * 8 < p.N) {
+                                    uint4 bb = ld_global_16B(p.bias + col0 + j8 * 8);
+                                    const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        v[j8 * 8 + 2 * e] += bf16_lo(bw[e]);
+                                        v[j8 * 8 + 2 * e + 1] += bf16_hi(bw[e]);
+                                    }
+                                }
+                            }
+                        }
+                        if (epi == B2D_EPI_F32_STORE) {
+                            float* o = reinterpret_cast<float*>(p.out) + cbase + (long long)row * p.ldc + col0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                if (col0 + j < p.N)
+                                    *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+                            float v2[32];
+                            bool has2 = false;
+                            if (epi == B2D_EPI_GELU || epi == B2D_EPI_SILU) {
+                                has2 = p.out2 != nullptr;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    v2[j] = v[j];
+                                    v[j] = (epi == B2D_EPI_GELU) ? gelu_tanh(v[j]) : silu(v[j]);
+                                }
+                            } else if (epi == B2D_EPI_GATE_RES) {
+                                const __nv_bfloat16* rp = p.res + (long long)row * p.ldres + col0;
+#pragma unroll
+                                for (int j8 = 0; j8 < 4; ++j8) {
+                                    if (col0 + j8 * 8 < p.N) {
+                                        uint4 rr = ld_global_16B(rp + j8 * 8);
+                                        const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+                                        float g[8];
+                                        if (p.gate_table != nullptr) {
+                                            uint4 gt = ld_global_16B(p.gate_table + col0 + j8 * 8);
+                                            uint4 ge = ld_global_16B(p.gate_temb + (long long)b * p.temb_stride + col0 + j8 * 8);
+                                            const uint32_t gtw[4] = {gt.x, gt.y, gt.z, gt.w};
+                                            const uint32_t gew[4] = {ge.x, ge.y, ge.z, ge.w};
+#pragma unroll
+                                            for (int e = 0; e < 4; ++e) {
+                                                g[2 * e] = bf16_lo(gtw[e]) + bf16_lo(gew[e]);
+                                                g[2 * e + 1] = bf16_hi(gtw[e]) + bf16_hi(gew[e]);
+                                            }
+                                        } else {
+#pragma unroll
+                                            for (int e = 0; e < 8; ++e) g[e] = 1.f;
+                                        }
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            v[j8 * 8 + 2 * e] = bf16_lo(rw[e]) + g[2 * e] * v[j8 * 8 + 2 * e];
+                                            v[j8 * 8 + 2 * e + 1] = bf16_hi(rw[e]) + g[2 * e + 1] * v[j8 * 8 + 2 * e + 1];
+                                        }
+                                        if (p.gate2_table != nullptr && p.out2 != nullptr) {
+                                            uint4 gt = ld_global_16B(p.gate2_table + col0 + j8 * 8);
+                                            uint4 ge = ld_global_16B(p.gate2_temb + (long long)b * p.temb_stride + col0 + j8 * 8);
+                                            const uint32_t gtw[4] = {gt.x, gt.y, gt.z, gt.w};
+                                            const uint32_t gew[4] = {ge.x, ge.y, ge.z, ge.w};
+#pragma unroll
+                                            for (int e = 0; e < 4; ++e) {
+                                                // the bf16-rounded primary output is what the next op sees
+                                                float a0 = __bfloat162float(__float2bfloat16_rn(v[j8 * 8 + 2 * e]));
+                                                float a1 = __bfloat162float(__float2bfloat16_rn(v[j8 * 8 + 2 * e + 1]));
+                                                v2[j8 * 8 + 2 * e] = a0 * (bf16_lo(gtw[e]) + bf16_lo(gew[e]));
+                                                v2[j8 * 8 + 2 * e + 1] = a1 * (bf16_hi(gtw[e]) + bf16_hi(gew[e]));
+                                            }
+                                        }
+                                    }
+                                }
+                                has2 = (p.gate2_table != nullptr && p.out2 != nullptr);
+                            } else if (epi == B2D_EPI_MUL_DGELU) {
+                                const __nv_bfloat16* ap = p.aux + (long long)row * p.ldaux + col0;
+#pragma unroll
+                                for (int j8 = 0; j8 < 4; ++j8) {
+                                    if (col0 + j8 * 8 < p.N) {
+                                        uint4 aa = ld_global_16B(ap + j8 * 8);
+                                        const uint32_t aw[4] = {aa.x, aa.y, aa.z, aa.w};
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            v[j8 * 8 + 2 * e] *= dgelu_tanh(bf16_lo(aw[e]));
+                                            v[j8 * 8 + 2 * e + 1] *= dgelu_tanh(bf16_hi(aw[e]));
+                                        }
+                                    }
+                                }
+                            }
+                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + cbase + (long long)row * p.ldc + col0;
+#pragma unroll
+                            for (int j8 = 0; j8 < 4; ++j8)
+                                if (col0 + j8 * 8 < p.N)
+                                    st_global_16B(o + j8 * 8, pack_bf16x2(v[j8 * 8], v[j8 * 8 + 1]),
+                                                  pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]),
+                                                  pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]),
+                                                  pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+                            if (has2) {
+                                __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + cbase + (long long)row * p.ldc2 + col0;
+#pragma unroll
+                                for (int j8 = 0; j8 < 4; ++j8)
+                                    if (col0 + j8 * 8 < p.N)
+                                        st_global_16B(o2 + j8 * 8, pack_bf16x2(v2[j8 * 8], v2[j8 * 8 + 1]),
+                                                      pack_bf16x2(v2[j8 * 8 + 2], v2[j8 * 8 + 3]),
+                                                      pack_bf16x2(v2[j8 * 8 + 4], v2[j8 * 8 + 5]),
+                                                      pack_bf16x2(v2[j8 * 8 + 6], v2[j8 * 8 + 7]));
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int BN, int A_MN, int B_MN>
+static int launch_gemm(const GemmKParams& kp, int grid, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto kern = gemm_kernel<BN, A_MN, B_MN>;
+    if (dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
+        attr_set[dev] = true;
+    }
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(kp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
+    return B2D_OK;
+}
+
+template <int BN>
+static int dispatch_major(const GemmKParams& kp, int a_mn, int b_mn, int grid, cudaStream_t s) {
+    if (!a_mn && !b_mn) return launch_gemm<BN, 0, 0>(kp, grid, s);
+    if (!a_mn && b_mn) return launch_gemm<BN, 0, 1>(kp, grid, s);
+    if (a_mn && b_mn) return launch_gemm<BN, 1, 1>(kp, grid, s);
+    return launch_gemm<BN, 1, 0>(kp, grid, s);
+}
+
+static int pick_block_n(int M, int N, int nsm, int work_mult) {
+    // minimise (waves * tile cost) over the candidate tile widths; cost ~ BN + fixed overhead
+    const int cands[4] = {256, 192, 128, 64};
+    int best = 128;
+    double best_t = 1e30;
+    int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    for (int i = 0; i < 4; ++i) {
+        int bn = cands[i];
+        if (bn > N && bn != 64 && (N % bn) != 0 && N < bn) continue;
+        int n_tiles = (N + bn - 1) / bn;
+        long long tiles = (long long)m_tiles * n_tiles * work_mult;
+        long long waves = (tiles + nsm - 1) / nsm;
+        double t = (double)waves * (bn + 24);  // +24: per-tile fixed cost (pipeline fill, epilogue tail)
+        if (t < best_t - 1e-9) {
+            best_t = t;
+            best = bn;
+        }
+    }
+    return best;
+}
+
+}  // namespace b2d
+
+using namespace b2d;
+
+extern "C" int b2d_gemm(const b2d_gemm_desc* d, void* stream_v) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    if (d == nullptr) return set_error(B2D_ERR_ARG, "gemm: null descriptor");
+    if (d->M <= 0 || d->N <= 0 || d->K <= 0) return set_error(B2D_ERR_SHAPE, "gemm: M,N,K must be positive");
+    if (d->N % 8 != 0) return set_error(B2D_ERR_SHAPE, "gemm: N %% 8 != 0 (N=%d)", d->N);
+    if (d->K2 % 64 != 0) return set_error(B2D_ERR_SHAPE, "gemm: K2 %% 64 != 0");
+    if ((d->lda % 8) || (d->ldb % 8)) return set_error(B2D_ERR_ALIGN, "gemm: lda/ldb must be multiples of 8 elements");
+    if (((uintptr_t)d->A & 15) || ((uintptr_t)d->B & 15) || ((uintptr_t)d->out & 15))
+        return set_error(B2D_ERR_ALIGN, "gemm: pointers must be 16-byte aligned");
+    const int splits = d->splits > 0 ? d->splits : 1;
+    const int batch = d->batch > 0 ? d->batch : 1;
+    const bool f32_atomic = d->epi == B2D_EPI_F32_ATOMIC || d->epi == B2D_EPI_F32_ATOMIC_T;
+    if (splits > 1 && !f32_atomic) return set_error(B2D_ERR_ARG, "gemm: split-K needs an atomic fp32 epilogue");
+    if (splits > 1 && d->K2 > 0) return set_error(B2D_ERR_ARG, "gemm: split-K with extension operands unsupported");
+    if (d->epi == B2D_EPI_GATE_RES && d->res == nullptr) return set_error(B2D_ERR_ARG, "gemm: GATE_RES needs res");
+    if (d->epi == B2D_EPI_MUL_DGELU && d->aux == nullptr) return set_error(B2D_ERR_ARG, "gemm: MUL_DGELU needs aux");
+    if (d->gate_table != nullptr && (d->gate_temb == nullptr || d->rows_per_sample <= 0))
+        return set_error(B2D_ERR_ARG, "gemm: gate needs temb + rows_per_sample");
+    if (d->K2 > 0 && d->a_mn_major) return set_error(B2D_ERR_ARG, "gemm: extension operands need K-major A");
+
+    int nsm = device_sm_count();
+    if (nsm <= 0) return B2D_ERR_CUDA;
+    int max_ctas = d->max_ctas > 0 ? d->max_ctas : nsm;
+    int bn = d->block_n > 0 ? d->block_n : pick_block_n(d->M, d->N, max_ctas, splits * batch);
+    if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return set_error(B2D_ERR_ARG, "gemm: bad block_n %d", bn);
+    if (d->a2_group_n > 0 && (d->a2_group_n % bn) != 0)
+        return set_error(B2D_ERR_ARG, "gemm: a2_group_n (%d) must be a multiple of block_n (%d)", d->a2_group_n, bn);
+
+    GemmKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    // ---- tensor maps. K-major operand [rows, K]: box {64, rows_tile}.  MN-major operand [K, cols]: box {64, 64}.
+    int rc;
+    // total extents seen by TMA: include batch offsets so every batch's window is in-bounds
+    {
+        long long rowsA = d->a_mn_major ? (long long)d->K + (batch - 1) * d->a_boff_row : (long long)d->M + (batch - 1) * d->a_boff_row;
+        long long colsA = d->a_mn_major ? (long long)d->M + (batch - 1) * d->a_boff_col : (long long)d->K + (batch - 1) * d->a_boff_col;
+        rc = make_tmap_2d(&kp.tmA, d->A, rowsA, colsA, d->lda, d->a_mn_major ? 64 : BLOCK_M, 64);
+        if (rc) return rc;
+        long long rowsB = d->b_mn_major ? (long long)d->K + (batch - 1) * d->b_boff_row : (long long)d->N + (batch - 1) * d->b_boff_row;
+        long long colsB = d->b_mn_major ? (long long)d->N + (batch - 1) * d->b_boff_col : (long long)d->K + (batch - 1) * d->b_boff_col;
+        rc = make_tmap_2d(&kp.tmB, d->B, rowsB, colsB, d->ldb, d->b_mn_major ? 64 : bn, 64);
+        if (rc) return rc;
+        if (d->K2 > 0) {
+            if (d->A2 == nullptr || d->B2 == nullptr) return set_error(B2D_ERR_ARG, "gemm: K2>0 needs A2,B2");
+            int groups = d->a2_group_n > 0 ? (d->N + d->a2_group_n - 1) / d->a2_group_n : 1;
+            rc = make_tmap_2d(&kp.tmA2, d->A2, d->M, (long long)d->K2 * groups, d->lda2, BLOCK_M, 64);
+            if (rc) return rc;
+            if (d->b_mn_major)
+                rc = make_tmap_2d(&kp.tmB2, d->B2, d->K2, d->N, d->ldb2, 64, 64);
+            else
+                rc = make_tmap_2d(&kp.tmB2, d->B2, d->N, d->K2, d->ldb2, bn, 64);
+            if (rc) return rc;
+        }
+    }
+    kp.M = d->M; kp.N = d->N; kp.K = d->K; kp.K2 = d->K2;
+    kp.a2_group_n = d->a2_group_n;
+    kp.splits = splits; kp.batch = batch;
+    kp.a_brow = (int)d->a_boff_row; kp.a_bcol = (int)d->a_boff_col;
+    kp.b_brow = (int)d->b_boff_row; kp.b_bcol = (int)d->b_boff_col;
+    kp.c_boff = d->c_boff;
+    kp.epi = d->epi;
+    kp.alpha = d->alpha == 0.f ? 1.f : d->alpha;
+    kp.out = d->out; kp.ldc = d->ldc;
+    kp.out2 = d->out2; kp.ldc2 = d->ldc2;
+    kp.bias = (const __nv_bfloat16*)d->bias;
+    kp.res = (const __nv_bfloat16*)d->res; kp.ldres = d->ldres;
+    kp.aux = (const __nv_bfloat16*)d->aux; kp.ldaux = d->ldaux;
+    kp.gate_table = (const __nv_bfloat16*)d->gate_table;
+    kp.gate_temb = (const __nv_bfloat16*)d->gate_temb;
+    kp.gate2_table = (const __nv_bfloat16*)d->gate2_table;
+    kp.gate2_temb = (const __nv_bfloat16*)d->gate2_temb;
+    kp.temb_stride = d->temb_stride;
+    kp.rows_per_sample = d->rows_per_sample;
+    kp.m_tiles = (d->M + BLOCK_M - 1) / BLOCK_M;
+    kp.n_tiles = (d->N + bn - 1) / bn;
+    kp.kb_main = (d->K + BLOCK_K - 1) / BLOCK_K;
+    kp.kb_ext = d->K2 / BLOCK_K;
+    if (splits > kp.kb_main) return set_error(B2D_ERR_ARG, "gemm: splits > k-blocks");
+    // every split must own at least one k-block
+    {
+        int per = (kp.kb_main + splits - 1) / splits;
+        if ((splits - 1) * per >= kp.kb_main) return set_error(B2D_ERR_ARG, "gemm: empty split (K=%d splits=%d)", d->K, splits);
+    }
+    long long total = (long long)kp.m_tiles * kp.n_tiles * splits * batch;
+    if (total > 0x7fffffffLL) return set_error(B2D_ERR_SHAPE, "gemm: too many tiles");
+    kp.total_work = (int)total;
+    int grid = (int)(total < max_ctas ? total : max_ctas);
+
+    switch (bn) {
+        case 64: return dispatch_major<64>(kp, d->a_mn_major, d->b_mn_major, grid, stream);
+        case 128: return dispatch_major<128>(kp, d->a_mn_major, d->b_mn_major, grid, stream);
+        case 192: return dispatch_major<192>(kp, d->a_mn_major, d->b_mn_major, grid, stream);
+        default: return dispatch_major<256>(kp, d->a_mn_major, d->b_mn_major, grid, stream);
+    }
+}

@@ -1,0 +1,33 @@
+// b2d_internal.h — host-side helpers shared by the .cu translation units of libb2d.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string.h>
+#include "../../include/b2d.h"
+
+namespace b2d {
+
+// printf-style; stores a thread-local message and returns `code`.
+int set_error(int code, const char* fmt, ...);
+
+// number of SMs of the current device (cached per device); <=0 on error
+int device_sm_count();
+
+// bf16 2-D tiled tensor map with 128-byte swizzle.  Tensor is row-major [rows, cols] with leading dimension `ld`
+// (elements).  Box = box_cols (inner, must be 64 => 128 B) x box_rows.
+int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_rows,
+                 int box_cols);
+
+// generic rank-N (N<=4) map: dims/strides innermost-first; strides in BYTES for dims 1..N-1; dtype bf16 or fp32.
+int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, int elem_bytes, int swizzle128);
+
+#define B2D_CHECK_LAUNCH(name)                                                                     \
+    do {                                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                                      \
+        if (e__ != cudaSuccess) return b2d::set_error(B2D_ERR_CUDA, "%s launch: %s", name, cudaGetErrorString(e__)); \
+    } while (0)
+
+}  // namespace b2d
