@@ -1,0 +1,589 @@
+"""B200-native LTX-Video DiT: the ``torch.nn.Module`` finetrainers' ``LTXVideoModelSpecification.forward`` calls
+(``/root/reference/finetrainers/models/ltx_video/base_specification.py:336-342``), re-implemented as one autograd node
+whose forward AND backward are sequences of libb2d kernels (tcgen05 GEMMs with fused epilogues, fused norm/modulate,
+q/k-norm + RoPE, tcgen05 attention) instead of the diffusers module graph
+(``/root/reference/finetrainers/patches/models/ltx_video/patch.py:38-127`` + diffusers ``LTXVideoTransformerBlock``).
+
+* Parameter FQNs are diffusers/peft compatible (``transformer_blocks.0.attn1.to_q.lora_A.default.weight`` ...), so
+  ``state_dict`` / LoRA export (``base_specification.py:379-397``) keep working.  The parameters are views into packed
+  device buffers (``[Wq;Wk;Wv]``, flat fp32 LoRA master / grad buffers) so the kernels see fused operands with no copies.
+* All block activations needed by backward are kept resident (≈5.5 GB at 49x512x768, B=1: trivial on 180 GB HBM3e), so
+  there is NO recompute pass, unlike the reference's ``checkpoint_wrapper`` (``utils/activation_checkpoint.py:40-49``).
+* The timestep embedding is evaluated on the B distinct timesteps, not on B*S rows (``patch.py:67-79`` flattens B*S).
+* LoRA (peft semantics: ``y = Wx + b + (alpha/r) B A x``) runs in the same tcgen05 accumulator as the base GEMM
+  (K-extension operands); master weights and gradients are fp32 (``trainer.py:130-136``), GEMM operands bf16.
+* There is no fallback: without libb2d.so / an sm_100 device every call raises.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, asdict
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+LORA_TARGETS = ("to_q", "to_k", "to_v", "to_out.0")  # examples/training/sft/ltx_video/crush_smol_lora/train.sh:77
+
+
+@dataclass
+class LTXConfig:
+    """``tests/models/ltx_video/_test_tp.py:29-59`` (real size)."""
+    in_channels: int = 128
+    out_channels: int = 128
+    patch_size: int = 1
+    patch_size_t: int = 1
+    num_attention_heads: int = 32
+    attention_head_dim: int = 64
+    cross_attention_dim: int = 2048
+    num_layers: int = 28
+    caption_channels: int = 4096
+    norm_eps: float = 1e-6
+    qk_norm_eps: float = 1e-5
+    ffn_mult: int = 4
+
+    @property
+    def inner_dim(self) -> int:
+        return self.num_attention_heads * self.attention_head_dim
+
+    def to_dict(self):
+        return asdict(self)
+
+
+class ParamLinear(nn.Module):
+    """Parameter container with nn.Linear's attribute names; the math happens in libb2d."""
+
+    def __init__(self, in_features, out_features, bias=True, dtype=torch.bfloat16, device=None):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = nn.Parameter(torch.empty(out_features, in_features, dtype=dtype, device=device))
+        self.bias = nn.Parameter(torch.empty(out_features, dtype=dtype, device=device)) if bias else None
+
+    def forward(self, *a, **k):
+        raise RuntimeError("ParamLinear holds parameters only; the b200 engine executes the fused step")
+
+
+class LoraLinear(nn.Module):
+    """peft-compatible naming: base_layer / lora_A.default / lora_B.default (fp32 adapters)."""
+
+    def __init__(self, base: ParamLinear, r: int, alpha: float):
+        super().__init__()
+        dev = base.weight.device
+        self.base_layer = base
+        self.lora_A = nn.ModuleDict({"default": ParamLinear(base.in_features, r, False, torch.float32, dev)})
+        self.lora_B = nn.ModuleDict({"default": ParamLinear(r, base.out_features, False, torch.float32, dev)})
+        self.r, self.lora_alpha, self.scaling = r, alpha, alpha / r
+        bound = 1.0 / math.sqrt(base.in_features)  # kaiming_uniform_(a=sqrt(5)) == U(-1/sqrt(fan_in), +)
+        with torch.no_grad():
+            self.lora_A["default"].weight.uniform_(-bound, bound)
+            self.lora_B["default"].weight.zero_()
+
+
+class _NormW(nn.Module):
+    def __init__(self, dim, dtype, device):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim, dtype=dtype, device=device))
+
+
+class _Attn(nn.Module):
+    def __init__(self, cfg: LTXConfig, dtype, device):
+        super().__init__()
+        d = cfg.inner_dim
+        self.norm_q = _NormW(d, dtype, device)
+        self.norm_k = _NormW(d, dtype, device)
+        self.to_q = ParamLinear(d, d, True, dtype, device)
+        self.to_k = ParamLinear(d, d, True, dtype, device)
+        self.to_v = ParamLinear(d, d, True, dtype, device)
+        self.to_out = nn.ModuleList([ParamLinear(d, d, True, dtype, device), nn.Dropout(0.0)])
+
+
+class _GELUProj(nn.Module):
+    def __init__(self, d_in, d_out, dtype, device):
+        super().__init__()
+        self.proj = ParamLinear(d_in, d_out, True, dtype, device)
+
+
+class _FF(nn.Module):
+    def __init__(self, d, mult, dtype, device):
+        super().__init__()
+        self.net = nn.ModuleList([_GELUProj(d, d * mult, dtype, device), nn.Dropout(0.0),
+                                  ParamLinear(d * mult, d, True, dtype, device)])
+
+
+class _Block(nn.Module):
+    def __init__(self, cfg: LTXConfig, dtype, device):
+        super().__init__()
+        d = cfg.inner_dim
+        self.norm1 = nn.Identity()
+        self.attn1 = _Attn(cfg, dtype, device)
+        self.norm2 = nn.Identity()
+        self.attn2 = _Attn(cfg, dtype, device)
+        self.ff = _FF(d, cfg.ffn_mult, dtype, device)
+        self.scale_shift_table = nn.Parameter(torch.empty(6, d, dtype=dtype, device=device))
+
+
+class _TimestepEmbedder(nn.Module):
+    def __init__(self, d, dtype, device):
+        super().__init__()
+        self.linear_1 = ParamLinear(256, d, True, dtype, device)
+        self.linear_2 = ParamLinear(d, d, True, dtype, device)
+
+
+class _Emb(nn.Module):
+    def __init__(self, d, dtype, device):
+        super().__init__()
+        self.timestep_embedder = _TimestepEmbedder(d, dtype, device)
+
+
+class _AdaSingle(nn.Module):
+    def __init__(self, d, dtype, device):
+        super().__init__()
+        self.emb = _Emb(d, dtype, device)
+        self.linear = ParamLinear(d, 6 * d, True, dtype, device)
+
+
+class _TextProj(nn.Module):
+    def __init__(self, c, d, dtype, device):
+        super().__init__()
+        self.linear_1 = ParamLinear(c, d, True, dtype, device)
+        self.linear_2 = ParamLinear(d, d, True, dtype, device)
+
+
+def _base(m):
+    return m.base_layer if isinstance(m, LoraLinear) else m
+
+
+class _StepFn(torch.autograd.Function):
+    """One autograd node for the whole 28-block stack (forward and hand-written backward)."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, hidden_states, encoder_hidden_states, tvals, key_bias, num_frames, height, width,
+                rope_scale):
+        ctx.model = model
+        return model._forward_impl(hidden_states, encoder_hidden_states, tvals, key_bias, num_frames, height, width,
+                                   rope_scale)
+
+    @staticmethod
+    def backward(ctx, dpred):
+        ctx.model._backward_impl(dpred)
+        return (None,) * 10
+
+
+class B200LTXTransformer(nn.Module):
+    def __init__(self, cfg: Optional[LTXConfig] = None, dtype=torch.bfloat16, device="cuda"):
+        super().__init__()
+        cfg = cfg or LTXConfig()
+        if cfg.attention_head_dim != 64:
+            raise ValueError("b200 attention kernels are specialised for attention_head_dim == 64")
+        if cfg.patch_size != 1 or cfg.patch_size_t != 1:
+            raise ValueError("LTX-Video uses patch_size = patch_size_t = 1")
+        if cfg.cross_attention_dim != cfg.inner_dim:
+            raise ValueError("cross_attention_dim must equal inner_dim (LTX-Video)")
+        self.cfg = cfg
+        self.config = cfg  # diffusers-style attribute
+        d = cfg.inner_dim
+        self.proj_in = ParamLinear(cfg.in_channels, d, True, dtype, device)
+        self.scale_shift_table = nn.Parameter(torch.empty(2, d, dtype=dtype, device=device))
+        self.time_embed = _AdaSingle(d, dtype, device)
+        self.caption_projection = _TextProj(cfg.caption_channels, d, dtype, device)
+        self.transformer_blocks = nn.ModuleList([_Block(cfg, dtype, device) for _ in range(cfg.num_layers)])
+        self.norm_out = nn.Identity()
+        self.proj_out = ParamLinear(d, cfg.out_channels, True, dtype, device)
+        self.gradient_checkpointing = False  # accepted for API compatibility; nothing is recomputed
+        self.lora_rank = 0
+        self.lora_scaling = 1.0
+        self._prepared = False
+        self._ws: Dict[Tuple, Dict[str, torch.Tensor]] = {}
+        self._rope: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._anchor = torch.zeros((), dtype=torch.float32, device=device, requires_grad=True)
+        self._saved_key = None
+        self.skip_block0_dx = True
+
+    # ------------------------------------------------------------------------------------------------
+    # adapters / packing
+    # ------------------------------------------------------------------------------------------------
+    def add_adapter(self, rank: int = 64, lora_alpha: Optional[float] = None, target_modules=LORA_TARGETS):
+        """``transformer.add_adapter(LoraConfig(r, lora_alpha, target_modules))`` (trainer.py:120-128)."""
+        if set(target_modules) != set(LORA_TARGETS):
+            raise NotImplementedError("b200 engine fuses LoRA on to_q|to_k|to_v|to_out.0 of attn1+attn2")
+        alpha = float(lora_alpha if lora_alpha is not None else rank)
+        for p in self.parameters():
+            p.requires_grad_(False)
+        for blk in self.transformer_blocks:
+            for attn in (blk.attn1, blk.attn2):
+                attn.to_q = LoraLinear(attn.to_q, rank, alpha)
+                attn.to_k = LoraLinear(attn.to_k, rank, alpha)
+                attn.to_v = LoraLinear(attn.to_v, rank, alpha)
+                attn.to_out[0] = LoraLinear(attn.to_out[0], rank, alpha)
+        self.lora_rank = rank
+        self.lora_scaling = alpha / rank
+        self._prepared = False
+
+    def lora_parameters(self) -> List[nn.Parameter]:
+        return [p for n, p in self.named_parameters() if "lora_" in n]
+
+    @torch.no_grad()
+    def prepare(self):
+        """Pack weights into the fused layouts the kernels consume and re-point the parameters into them."""
+        cfg = self.cfg
+        d = cfg.inner_dim
+        r = self.lora_rank
+        rp = ((r + 63) // 64) * 64 if r else 0
+        self.rpad = rp
+        dev = self.proj_in.weight.device
+        self._blk = []
+        # flat fp32 LoRA master + grad (padded rank) and bf16 operand copy
+        per_blk = (8 * rp * d) * 2 if r else 0  # A:[3rp+rp+rp+2rp+rp, d] ; B:[(3+1+1+2+1) d, rp]
+        nl = cfg.num_layers
+        if r:
+            self.lora_flat = torch.zeros(nl * per_blk, dtype=torch.float32, device=dev)
+            self.lora_grad_flat = torch.zeros_like(self.lora_flat)
+            self.lora_bf16 = torch.zeros(nl * per_blk, dtype=torch.bfloat16, device=dev)
+        for li, blk in enumerate(self.transformer_blocks):
+            a1, a2 = blk.attn1, blk.attn2
+            e = {}
+            # fused base weights; the module parameters become views of the packed storage
+            def pack(mods):
+                w = torch.cat([_base(m).weight.data for m in mods], 0).contiguous()
+                bvec = torch.cat([_base(m).bias.data for m in mods], 0).contiguous()
+                o = 0
+                for m in mods:
+                    n = _base(m).out_features
+                    _base(m).weight.data = w[o:o + n]
+                    _base(m).bias.data = bvec[o:o + n]
+                    o += n
+                return w, bvec
+            e["Wqkv"], e["bqkv"] = pack([a1.to_q, a1.to_k, a1.to_v])
+            e["Wo"], e["bo"] = _base(a1.to_out[0]).weight.data, _base(a1.to_out[0]).bias.data
+            e["Wq2"], e["bq2"] = _base(a2.to_q).weight.data, _base(a2.to_q).bias.data
+            e["Wkv2"], e["bkv2"] = pack([a2.to_k, a2.to_v])
+            e["Wo2"], e["bo2"] = _base(a2.to_out[0]).weight.data, _base(a2.to_out[0]).bias.data
+            e["W1"], e["b1"] = blk.ff.net[0].proj.weight.data, blk.ff.net[0].proj.bias.data
+            e["W2"], e["b2"] = blk.ff.net[2].weight.data, blk.ff.net[2].bias.data
+            e["nq1"], e["nk1"] = a1.norm_q.weight.data, a1.norm_k.weight.data
+            e["nq2"], e["nk2"] = a2.norm_q.weight.data, a2.norm_k.weight.data
+            e["sst"] = blk.scale_shift_table.data
+            if r:
+                base = li * per_blk
+                off = [base]
+
+                def carve(rows, cols):
+                    n = rows * cols
+                    s = off[0]
+                    off[0] += n
+                    return (self.lora_flat[s:s + n].view(rows, cols), self.lora_grad_flat[s:s + n].view(rows, cols),
+                            self.lora_bf16[s:s + n].view(rows, cols))
+
+                groups = {"qkv": [a1.to_q, a1.to_k, a1.to_v], "o": [a1.to_out[0]], "q2": [a2.to_q],
+                          "kv2": [a2.to_k, a2.to_v], "o2": [a2.to_out[0]]}
+                for gname, mods in groups.items():
+                    n_ad = len(mods)
+                    A, gA, Ab = carve(n_ad * rp, d)
+                    Bm, gB, Bb = carve(n_ad * d, rp)
+                    for j, m in enumerate(mods):
+                        A[j * rp:j * rp + r].copy_(m.lora_A["default"].weight.data)
+                        Bm[j * d:(j + 1) * d, :r].copy_(m.lora_B["default"].weight.data)
+                        m.lora_A["default"].weight.data = A[j * rp:j * rp + r]
+                        m.lora_B["default"].weight.data = Bm[j * d:(j + 1) * d, :r]
+                        m.lora_A["default"].weight.grad = gA[j * rp:j * rp + r]
+                        m.lora_B["default"].weight.grad = gB[j * d:(j + 1) * d, :r]
+                    e["A_" + gname], e["gA_" + gname], e["Ab_" + gname] = A, gA, Ab
+                    e["B_" + gname], e["gB_" + gname], e["Bb_" + gname] = Bm, gB, Bb
+            self._blk.append(e)
+        self._prepared = True
+        self._ws.clear()
+        return self
+
+    def _attach_lora_grads(self):
+        """(Re-)attach .grad views after an external ``zero_grad(set_to_none=True)``; returns True if any was missing."""
+        missing = False
+        for e, blk in zip(self._blk, self.transformer_blocks):
+            a1, a2 = blk.attn1, blk.attn2
+            groups = {"qkv": [a1.to_q, a1.to_k, a1.to_v], "o": [a1.to_out[0]], "q2": [a2.to_q],
+                      "kv2": [a2.to_k, a2.to_v], "o2": [a2.to_out[0]]}
+            d, r, rp = self.cfg.inner_dim, self.lora_rank, self.rpad
+            for gname, mods in groups.items():
+                for j, m in enumerate(mods):
+                    pa, pb = m.lora_A["default"].weight, m.lora_B["default"].weight
+                    if pa.grad is None or pb.grad is None:
+                        missing = True
+                        pa.grad = e["gA_" + gname][j * rp:j * rp + r]
+                        pb.grad = e["gB_" + gname][j * d:(j + 1) * d, :r]
+        return missing
+
+    # ------------------------------------------------------------------------------------------------
+    # workspace
+    # ------------------------------------------------------------------------------------------------
+    def _workspace(self, B, S, L):
+        key = (B, S, L)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        cfg = self.cfg
+        d, H, nl, rp = cfg.inner_dim, cfg.num_attention_heads, cfg.num_layers, self.rpad
+        R, RL = B * S, B * L
+        dev = self.proj_in.weight.device
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        ws = {}
+
+        def z(name, *shape, kw=bf):
+            ws[name] = torch.zeros(*shape, **kw)
+
+        # embeds
+        z("tsin", B, 256); z("t1", B, d); z("t2s", B, d); z("embedded", B, d); z("temb", B, 6 * d)
+        z("c1", RL, d); z("enc", RL, d)
+        # per-block saved activations
+        z("h", nl + 1, R, d)            # h[l] = input of block l; h[nl] = final hidden
+        z("n1", nl, R, d); z("qkv", nl, R, 3 * d)
+        z("qh", nl, B, H, S, 64); z("kh", nl, B, H, S, 64); z("vh", nl, B, H, S, 64)
+        z("ao", nl, R, d); z("lse", nl, B, H, S, kw=f32)
+        z("h1", nl, R, d); z("q2", nl, R, d); z("q2h", nl, B, H, S, 64)
+        z("kv2", nl, RL, 2 * d); z("k2h", nl, B, H, L, 64); z("v2h", nl, B, H, L, 64)
+        z("ao2", nl, R, d); z("lse2", nl, B, H, S, kw=f32)
+        z("h2", nl, R, d); z("ffpre", nl, R, cfg.ffn_mult * d)
+        if rp:
+            z("u_qkv", nl, R, 3 * rp); z("u_o", nl, R, rp); z("u_q2", nl, R, rp); z("u_kv2", nl, RL, 2 * rp)
+            z("u_o2", nl, R, rp)
+            z("du_big", R, 3 * rp); z("du_txt", RL, 2 * rp)
+        # scratch shared by all blocks
+        z("n2", R, d); z("f", R, cfg.ffn_mult * d); z("y", R, d); z("pred", R, cfg.out_channels)
+        z("dh", R, d); z("g", R, d); z("dwide", R, cfg.ffn_mult * d); z("dn", R, d); z("da", R, d)
+        z("dqh", B, H, S, 64); z("dkh", B, H, S, 64); z("dvh", B, H, S, 64)
+        z("dk2h", B, H, L, 64); z("dv2h", B, H, L, 64)
+        z("dqkv", R, 3 * d); z("dq2", R, d); z("dkv2", RL, 2 * d)
+        z("delta", B, H, S, kw=f32)
+        self._ws[key] = ws
+        return ws
+
+    def _rope_tables(self, Fr, Hh, Ww, rope_scale):
+        key = (Fr, Hh, Ww, tuple(float(x) for x in rope_scale))
+        t = self._rope.get(key)
+        if t is None:
+            d = self.cfg.inner_dim
+            dev = self.proj_in.weight.device
+            cos = torch.empty(Fr * Hh * Ww, d, dtype=torch.float32, device=dev)
+            sin = torch.empty_like(cos)
+            # diffusers LTXVideoRotaryPosEmbed: grid * scale * patch / base (base_num_frames 20, base_h = base_w = 2048)
+            ops.rope_table(cos, sin, Fr, Hh, Ww, d, rope_scale[0] * self.cfg.patch_size_t / 20.0,
+                           rope_scale[1] * self.cfg.patch_size / 2048.0, rope_scale[2] * self.cfg.patch_size / 2048.0)
+            t = (cos, sin)
+            self._rope[key] = t
+        return t
+
+    # ------------------------------------------------------------------------------------------------
+    # public forward (diffusers signature; patch.py:38-51)
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, hidden_states, encoder_hidden_states, timestep, encoder_attention_mask=None, num_frames=None,
+                height=None, width=None, rope_interpolation_scale=None, return_dict=False, **kwargs):
+        if not self._prepared:
+            self.prepare()
+        B = hidden_states.shape[0]
+        # finetrainers passes per-token timesteps that are constant per sample (base_specification.py:319-320)
+        tvals = timestep.reshape(B, -1)[:, 0].to(torch.float32).contiguous()
+        key_bias = None
+        if encoder_attention_mask is not None:
+            m = encoder_attention_mask
+            if m.ndim == 3:
+                m = m[:, 0]
+            key_bias = ((1.0 - m.to(torch.float32)) * -10000.0).contiguous()  # patch.py:55-57
+        if rope_interpolation_scale is None:
+            rope_interpolation_scale = (1.0, 1.0, 1.0)
+        out = _StepFn.apply(self._anchor, self, hidden_states, encoder_hidden_states, tvals, key_bias, int(num_frames),
+                            int(height), int(width), tuple(float(x) for x in rope_interpolation_scale))
+        return (out,)
+
+    # ------------------------------------------------------------------------------------------------
+    # forward implementation
+    # ------------------------------------------------------------------------------------------------
+    def refresh_lora_operands(self):
+        """fp32 master -> bf16 GEMM operands (one flat cast per step)."""
+        if self.lora_rank:
+            ops.cast_f32_bf16(self.lora_flat, self.lora_bf16, self.lora_flat.numel(), 1.0)
+
+    def _lin(self, x, W, bias, out, M, N, K, lora=None, **kw):
+        """out = epi(x W^T + bias [+ u B^T]);  lora = (Ab [n*rp,K], Bb [N,rp], u [M,n*rp], n_ad)."""
+        if lora is not None:
+            Ab, Bb, u, n_ad = lora
+            rp = self.rpad
+            ops.gemm(x, Ab, u, M=M, N=n_ad * rp, K=K, alpha=self.lora_scaling)
+            ops.gemm(x, W, out, M=M, N=N, K=K, bias=bias, A2=u, B2=Bb, K2=rp, a2_group_n=(N // n_ad if n_ad > 1 else 0),
+                     **kw)
+        else:
+            ops.gemm(x, W, out, M=M, N=N, K=K, bias=bias, **kw)
+
+    def _forward_impl(self, hidden_states, ehs, tvals, key_bias, Fr, Hh, Ww, rope_scale):
+        cfg = self.cfg
+        d, H, nl, rp = cfg.inner_dim, cfg.num_attention_heads, cfg.num_layers, self.rpad
+        B, S, Cin = hidden_states.shape
+        L = ehs.shape[1]
+        assert S == Fr * Hh * Ww, "sequence length must equal num_frames*height*width (patch size 1)"
+        R, RL = B * S, B * L
+        ws = self._workspace(B, S, L)
+        self._saved_key = (B, S, L, Fr, Hh, Ww, rope_scale)
+        self._key_bias = key_bias
+        cos, sin = self._rope_tables(Fr, Hh, Ww, rope_scale)
+        x_in = hidden_states.reshape(R, Cin).to(torch.bfloat16).contiguous()
+        ehs2 = ehs.reshape(RL, cfg.caption_channels).to(torch.bfloat16).contiguous()
+        self.refresh_lora_operands()
+        te = self.time_embed
+        # ---- timestep embedding on the B distinct timesteps (K2)
+        ops.timestep_sinusoid(tvals, ws["tsin"], B)
+        ops.gemm(ws["tsin"], te.emb.timestep_embedder.linear_1.weight, ws["t1"], M=B, N=d, K=256,
+                 bias=te.emb.timestep_embedder.linear_1.bias, epi=ops.EPI_SILU)
+        ops.gemm(ws["t1"], te.emb.timestep_embedder.linear_2.weight, ws["t2s"], M=B, N=d, K=d,
+                 bias=te.emb.timestep_embedder.linear_2.bias, epi=ops.EPI_SILU, out2=ws["embedded"])
+        ops.gemm(ws["t2s"], te.linear.weight, ws["temb"], M=B, N=6 * d, K=d, bias=te.linear.bias)
+        temb = ws["temb"]
+        # ---- caption projection (K3), patch embed (K1)
+        cp = self.caption_projection
+        ops.gemm(ehs2, cp.linear_1.weight, ws["c1"], M=RL, N=d, K=cfg.caption_channels, bias=cp.linear_1.bias,
+                 epi=ops.EPI_GELU)
+        ops.gemm(ws["c1"], cp.linear_2.weight, ws["enc"], M=RL, N=d, K=d, bias=cp.linear_2.bias)
+        enc = ws["enc"]
+        ops.gemm(x_in, self.proj_in.weight, ws["h"][0], M=R, N=d, K=Cin, bias=self.proj_in.bias)
+        scale = 1.0 / math.sqrt(cfg.attention_head_dim)
+        for l in range(nl):
+            e = self._blk[l]
+            sst = e["sst"]
+            h_in, n1 = ws["h"][l], ws["n1"][l]
+            # K5: RMSNorm + modulate (shift_msa = row 0, scale_msa = row 1)
+            ops.norm_modulate_fwd(h_in, n1, sst[0], temb[:, 0:], sst[1], temb[:, d:], 6 * d, R, d, S, cfg.norm_eps)
+            # K6: fused QKV (+LoRA)
+            self._lin(n1, e["Wqkv"], e["bqkv"], ws["qkv"][l], R, 3 * d, d,
+                      lora=(e["Ab_qkv"], e["Bb_qkv"], ws["u_qkv"][l], 3) if rp else None)
+            # K7: q/k RMSNorm + RoPE + head split
+            ops.qknorm_rope_fwd(ws["qkv"][l], 3 * d, 0, e["nq1"], cos, sin, ws["qh"][l], B, S, H, True, cfg.qk_norm_eps)
+            ops.qknorm_rope_fwd(ws["qkv"][l], 3 * d, d, e["nk1"], cos, sin, ws["kh"][l], B, S, H, True, cfg.qk_norm_eps)
+            ops.qknorm_rope_fwd(ws["qkv"][l], 3 * d, 2 * d, None, None, None, ws["vh"][l], B, S, H, False, cfg.qk_norm_eps)
+            # K8: self attention
+            ops.attn_fwd(ws["qh"][l], ws["kh"][l], ws["vh"][l], None, ws["ao"][l], ws["lse"][l], B, H, S, S, scale)
+            # K9: out proj + gated residual (gate_msa = row 2)
+            self._lin(ws["ao"][l], e["Wo"], e["bo"], ws["h1"][l], R, d, d,
+                      lora=(e["Ab_o"], e["Bb_o"], ws["u_o"][l], 1) if rp else None,
+                      epi=ops.EPI_GATE_RES, res=h_in, gate_table=sst[2], gate_temb=temb[:, 2 * d:], temb_stride=6 * d,
+                      rows_per_sample=S)
+            # K10: cross attention (no pre-norm, no gate)
+            h1 = ws["h1"][l]
+            self._lin(h1, e["Wq2"], e["bq2"], ws["q2"][l], R, d, d,
+                      lora=(e["Ab_q2"], e["Bb_q2"], ws["u_q2"][l], 1) if rp else None)
+            self._lin(enc, e["Wkv2"], e["bkv2"], ws["kv2"][l], RL, 2 * d, d,
+                      lora=(e["Ab_kv2"], e["Bb_kv2"], ws["u_kv2"][l], 2) if rp else None)
+            ops.qknorm_rope_fwd(ws["q2"][l], d, 0, e["nq2"], None, None, ws["q2h"][l], B, S, H, True, cfg.qk_norm_eps)
+            ops.qknorm_rope_fwd(ws["kv2"][l], 2 * d, 0, e["nk2"], None, None, ws["k2h"][l], B, L, H, True, cfg.qk_norm_eps)
+            ops.qknorm_rope_fwd(ws["kv2"][l], 2 * d, d, None, None, None, ws["v2h"][l], B, L, H, False, cfg.qk_norm_eps)
+            ops.attn_fwd(ws["q2h"][l], ws["k2h"][l], ws["v2h"][l], key_bias, ws["ao2"][l], ws["lse2"][l], B, H, S, L, scale)
+            self._lin(ws["ao2"][l], e["Wo2"], e["bo2"], ws["h2"][l], R, d, d,
+                      lora=(e["Ab_o2"], e["Bb_o2"], ws["u_o2"][l], 1) if rp else None,
+                      epi=ops.EPI_GATE_RES, res=h1)
+            # K11/K12: norm2 + modulate (rows 3,4), FFN with GELU epilogue, gated residual (row 5)
+            h2 = ws["h2"][l]
+            ops.norm_modulate_fwd(h2, ws["n2"], sst[3], temb[:, 3 * d:], sst[4], temb[:, 4 * d:], 6 * d, R, d, S,
+                                  cfg.norm_eps)
+            ops.gemm(ws["n2"], e["W1"], ws["f"], M=R, N=cfg.ffn_mult * d, K=d, bias=e["b1"], epi=ops.EPI_GELU,
+                     out2=ws["ffpre"][l])
+            ops.gemm(ws["f"], e["W2"], ws["h"][l + 1], M=R, N=d, K=cfg.ffn_mult * d, bias=e["b2"], epi=ops.EPI_GATE_RES,
+                     res=h2, gate_table=sst[5], gate_temb=temb[:, 5 * d:], temb_stride=6 * d, rows_per_sample=S)
+        # K13: final LayerNorm + modulate (table rows 0 = shift, 1 = scale; embedded_timestep), proj_out
+        t2 = self.scale_shift_table.data
+        ops.norm_modulate_fwd(ws["h"][nl], ws["y"], t2[0], ws["embedded"], t2[1], ws["embedded"], d, R, d, S, 1e-6, True)
+        ops.gemm(ws["y"], self.proj_out.weight, ws["pred"], M=R, N=cfg.out_channels, K=d, bias=self.proj_out.bias)
+        return ws["pred"].view(B, S, cfg.out_channels)
+
+    # ------------------------------------------------------------------------------------------------
+    # backward implementation (LoRA: dX through every op, dW only for adapters)
+    # ------------------------------------------------------------------------------------------------
+    def _splits(self, tiles, kb):
+        sm = 148
+        s = max(1, min(kb, sm // max(1, tiles)))
+        per = -(-kb // s)
+        return -(-kb // per)
+
+    def _lora_bwd(self, dy, x, u, du, e, g, M, N, K, n_ad):
+        """dy [M,N] (N = n_ad*Nj), x [M,K], u [M,n_ad*rp] (already scaled).  Fills du, accumulates gA/gB."""
+        rp = self.rpad
+        Nj = N // n_ad
+        kb = -(-M // 64)
+        du = du.view(-1)[:M * n_ad * rp].view(M, n_ad * rp)
+        # du_j = s * dy_j B_j
+        ops.gemm(dy, e["Bb_" + g], du, M=M, N=rp, K=Nj, b_mn=True, batch=n_ad, a_boff=(0, Nj), b_boff=(Nj, 0),
+                 c_boff=rp, ldc=n_ad * rp, alpha=self.lora_scaling)
+        # dB_j += dy_j^T u_j
+        ops.gemm(dy, u, e["gB_" + g], M=Nj, N=rp, K=M, a_mn=True, b_mn=True, batch=n_ad, a_boff=(0, Nj), b_boff=(0, rp),
+                 c_boff=Nj * rp, ldc=rp, epi=ops.EPI_F32_ATOMIC, block_n=64 if rp == 64 else 128,
+                 splits=self._splits(-(-Nj // 128) * n_ad * (rp // (64 if rp == 64 else 128)), kb))
+        # dA += du^T x   (computed as (x^T du)^T)
+        ops.gemm(x, du, e["gA_" + g], M=K, N=n_ad * rp, K=M, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC_T, ldc=K,
+                 block_n=64, splits=self._splits(-(-K // 128) * (n_ad * rp // 64), kb))
+        return du
+
+    def _backward_impl(self, dpred):
+        cfg = self.cfg
+        d, H, nl, rp = cfg.inner_dim, cfg.num_attention_heads, cfg.num_layers, self.rpad
+        B, S, L, Fr, Hh, Ww, rope_scale = self._saved_key
+        R, RL = B * S, B * L
+        ws = self._workspace(B, S, L)
+        cos, sin = self._rope_tables(Fr, Hh, Ww, rope_scale)
+        key_bias = self._key_bias
+        temb = ws["temb"]
+        scale = 1.0 / math.sqrt(cfg.attention_head_dim)
+        if not rp:
+            raise NotImplementedError("full-rank fine-tuning backward (base dW) is not built yet; use add_adapter()")
+        if self._attach_lora_grads():
+            self.lora_grad_flat.zero_()
+        dp = dpred.reshape(R, cfg.out_channels).to(torch.bfloat16).contiguous()
+        # head: dy = dpred Wout ; dh = LN-modulate bwd ; g = dh * gate_mlp(last block)
+        ops.gemm(dp, self.proj_out.weight, ws["dn"], M=R, N=d, K=cfg.out_channels, b_mn=True)
+        t2 = self.scale_shift_table.data
+        last = self._blk[nl - 1]["sst"]
+        ops.norm_modulate_bwd(ws["dn"], ws["h"][nl], None, ws["dh"], t2[1], ws["embedded"], d, R, d, S, 1e-6, True)
+        # (embedded has stride d, temb stride 6d: the gate of the last block is applied by a separate colscale)
+        ops.colscale(ws["dh"], ws["g"], last[5], temb[:, 5 * d:], 6 * d, R, d, S)
+        dh, g = ws["dh"], ws["g"]
+        for l in range(nl - 1, -1, -1):
+            e = self._blk[l]
+            sst = e["sst"]
+            # ---- FFN: dfp = (g W2) * gelu'(pre) ; dn2 = dfp W1 ; dh2 = dh + norm_bwd(dn2; h2, scale_mlp=row 4)
+            ops.gemm(g, e["W2"], ws["dwide"], M=R, N=cfg.ffn_mult * d, K=d, b_mn=True, epi=ops.EPI_MUL_DGELU,
+                     aux=ws["ffpre"][l])
+            ops.gemm(ws["dwide"], e["W1"], ws["dn"], M=R, N=d, K=cfg.ffn_mult * d, b_mn=True)
+            ops.norm_modulate_bwd(ws["dn"], ws["h2"][l], dh, dh, sst[4], temb[:, 4 * d:], 6 * d, R, d, S, cfg.norm_eps)
+            # ---- cross attention out-proj (no gate): da2 = dh W_o2 + du A ; LoRA grads
+            du = self._lora_bwd(dh, ws["ao2"][l], ws["u_o2"][l], ws["du_big"], e, "o2", R, d, d, 1)
+            ops.gemm(dh, e["Wo2"], ws["da"], M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_o2"], K2=rp)
+            ops.attn_bwd(ws["q2h"][l], ws["k2h"][l], ws["v2h"][l], key_bias, ws["ao2"][l], ws["da"], ws["lse2"][l],
+                         ws["delta"], ws["dqh"], ws["dk2h"], ws["dv2h"], B, H, S, L, scale)
+            ops.qknorm_rope_bwd(ws["dqh"], ws["q2"][l], d, 0, e["nq2"], None, None, ws["dq2"], d, 0, B, S, H, True,
+                                cfg.qk_norm_eps)
+            ops.qknorm_rope_bwd(ws["dk2h"], ws["kv2"][l], 2 * d, 0, e["nk2"], None, None, ws["dkv2"], 2 * d, 0, B, L, H,
+                                True, cfg.qk_norm_eps)
+            ops.qknorm_rope_bwd(ws["dv2h"], ws["kv2"][l], 2 * d, d, None, None, None, ws["dkv2"], 2 * d, d, B, L, H, False,
+                                cfg.qk_norm_eps)
+            self._lora_bwd(ws["dkv2"], ws["enc"], ws["u_kv2"][l], ws["du_txt"], e, "kv2", RL, 2 * d, d, 2)
+            du = self._lora_bwd(ws["dq2"], ws["h1"][l], ws["u_q2"][l], ws["du_big"], e, "q2", R, d, d, 1)
+            # dh1 = dh2 + dq2 W_q2 + du A ; g = dh1 * gate_msa (row 2)
+            ops.gemm(ws["dq2"], e["Wq2"], dh, M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_q2"], K2=rp,
+                     epi=ops.EPI_GATE_RES, res=dh, gate2_table=sst[2], gate2_temb=temb[:, 2 * d:], out2=g,
+                     temb_stride=6 * d, rows_per_sample=S)
+            # ---- self attention out-proj (gated): dattn = g W_o + du A
+            du = self._lora_bwd(g, ws["ao"][l], ws["u_o"][l], ws["du_big"], e, "o", R, d, d, 1)
+            ops.gemm(g, e["Wo"], ws["da"], M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_o"], K2=rp)
+            ops.attn_bwd(ws["qh"][l], ws["kh"][l], ws["vh"][l], None, ws["ao"][l], ws["da"], ws["lse"][l], ws["delta"],
+                         ws["dqh"], ws["dkh"], ws["dvh"], B, H, S, S, scale)
+            ops.qknorm_rope_bwd(ws["dqh"], ws["qkv"][l], 3 * d, 0, e["nq1"], cos, sin, ws["dqkv"], 3 * d, 0, B, S, H, True,
+                                cfg.qk_norm_eps)
+            ops.qknorm_rope_bwd(ws["dkh"], ws["qkv"][l], 3 * d, d, e["nk1"], cos, sin, ws["dqkv"], 3 * d, d, B, S, H, True,
+                                cfg.qk_norm_eps)
+            ops.qknorm_rope_bwd(ws["dvh"], ws["qkv"][l], 3 * d, 2 * d, None, None, None, ws["dqkv"], 3 * d, 2 * d, B, S, H,
+                                False, cfg.qk_norm_eps)
+            du = self._lora_bwd(ws["dqkv"], ws["n1"][l], ws["u_qkv"][l], ws["du_big"], e, "qkv", R, 3 * d, d, 3)
+            if l == 0 and self.skip_block0_dx:
+                break  # nothing trainable upstream of block 0's adapters (proj_in / embeds are frozen)
+            ops.gemm(ws["dqkv"], e["Wqkv"], ws["dn"], M=R, N=d, K=3 * d, b_mn=True, A2=du, B2=e["Ab_qkv"], K2=3 * rp)
+            # dh0 = dh1 + norm_bwd(dn1; h_in, scale_msa=row 1) ; g = dh0 * gate_mlp of block l-1
+            prev = self._blk[l - 1]["sst"] if l > 0 else None
+            ops.norm_modulate_bwd(ws["dn"], ws["h"][l], dh, dh, sst[1], temb[:, d:], 6 * d, R, d, S, cfg.norm_eps,
+                                  gate2_tab=prev[5] if l > 0 else None, gate2_emb=temb[:, 5 * d:] if l > 0 else None,
+                                  out2=g if l > 0 else None)

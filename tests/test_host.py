@@ -1,0 +1,139 @@
+"""CPU: host-side logic of the b200 package — C ABI surface, parameter packing / FQNs, sigma sampling, provider
+registry, and the world_size-2 gloo path of the parallel backend."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from finetrainers_b200 import lib
+    path = lib.build()
+    so = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "b2d.h")).read()
+    declared = set(re.findall(r"\b(b2d_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
+    for name in declared:
+        assert hasattr(so, name), f"{name} declared in include/b2d.h but not exported"
+    so.b2d_version.restype = ctypes.c_int
+    assert so.b2d_version() == 1
+
+
+def test_ops_fail_loudly_without_cuda():
+    from finetrainers_b200 import ops, lib
+    x = torch.zeros(8, 8, dtype=torch.bfloat16)
+    with pytest.raises(lib.B2DError):
+        ops.colscale(x, x, x[0], x, 8, 8, 8, 8)
+
+
+def test_model_fqns_match_oracle_and_packing_is_lossless():
+    from oracle import ltx_oracle as O
+    from finetrainers_b200.model import B200LTXTransformer, LTXConfig
+    cfgk = dict(in_channels=32, out_channels=32, num_attention_heads=2, attention_head_dim=64, cross_attention_dim=128,
+                num_layers=2, caption_channels=64)
+    om = O.LTXTransformerOracle(O.LTXConfig(**cfgk))
+    O.add_lora(om, 16, 32)
+    O.synthetic_init_(om)
+    bm = B200LTXTransformer(LTXConfig(**cfgk), torch.bfloat16, "cpu")
+    bm.add_adapter(16, 32)
+    assert [n for n, _ in bm.named_parameters()] == [n for n, _ in om.named_parameters()] or \
+        set(n for n, _ in bm.named_parameters()) == set(n for n, _ in om.named_parameters())
+    bm.load_state_dict(om.state_dict(), strict=True)
+    before = {k: v.clone() for k, v in bm.state_dict().items()}
+    bm.prepare()
+    after = bm.state_dict()
+    for k in before:
+        assert torch.equal(before[k], after[k]), k
+    # fused views: q/k/v weights are consecutive rows of one buffer; LoRA params are views of the flat fp32 buffer
+    e = bm._blk[0]
+    a1 = bm.transformer_blocks[0].attn1
+    assert a1.to_k.base_layer.weight.data_ptr() == e["Wqkv"][128:].data_ptr()
+    assert a1.to_q.lora_A["default"].weight.dtype == torch.float32
+    assert bm.rpad == 64 and bm.lora_scaling == 2.0
+    assert a1.to_v.lora_B["default"].weight.shape == (128, 16)
+    n_lora = sum(p.numel() for p in bm.lora_parameters())
+    assert n_lora == 2 * 8 * 16 * 128 * 2
+    # padded entries of the flat buffer are exactly zero
+    assert bm.lora_flat.abs().sum() > 0
+    assert torch.count_nonzero(bm.lora_flat).item() <= n_lora
+    # only adapters train
+    assert all(("lora_" in n) == p.requires_grad for n, p in bm.named_parameters())
+
+
+def test_sigma_sampling_matches_reference_golden(golden):
+    from finetrainers_b200.trainer import prepare_sigmas, prepare_loss_weights
+    from finetrainers_b200.specification import FlowMatchSchedulerTable
+    sch = FlowMatchSchedulerTable()
+    assert torch.equal(sch.sigmas, golden["sig_table"])
+    for scheme in ("none", "logit_normal", "mode"):
+        gen = torch.Generator().manual_seed(1234)
+        s = prepare_sigmas(sch, sch.sigmas, 16, 1000, scheme, 0.0, 1.0, 1.29, "cpu", gen)
+        assert torch.equal(s, golden[f"sig_{scheme}"])
+    sig = torch.tensor([0.25, 0.5])
+    assert torch.equal(prepare_loss_weights(sig, "none"), torch.ones(2))
+    assert torch.allclose(prepare_loss_weights(sig, "sigma_sqrt"), torch.tensor([16.0, 4.0]))
+
+
+def test_attention_provider_registry_api():
+    from finetrainers_b200 import attention as A
+    assert A.AttentionProvider.B200 in A._AttentionProviderRegistry.list_providers()
+    name, fn = A._AttentionProviderRegistry.get_active_provider()
+    assert name == A.AttentionProvider.B200
+    assert {"query", "key", "value", "attn_mask", "scale"} <= A._AttentionProviderRegistry._supported_arg_names[name]
+    with A.attention_provider(A.AttentionProvider.B200):
+        pass
+    with pytest.raises(ValueError):
+        with A.attention_provider("flash"):
+            pass
+    assert not A._AttentionProviderRegistry.supports_context_parallel(A.AttentionProvider.B200)
+    # constraint checks raise ValueError like the reference's (_check_device/_check_shape)
+    q = torch.zeros(1, 2, 8, 64, dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        A._check_b200(q, q, q)
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["B2D_ROOT"])
+from finetrainers_b200.parallel import B200ParallelBackend, allreduce_flat_grads, fused_step_metrics, dist_mean, dist_max
+be = B200ParallelBackend(backend="gloo", device_type="cpu")
+assert be.world_size == 2 and be.data_replication_enabled and not be.data_sharding_enabled
+r = be.rank
+m = torch.nn.Linear(4, 4)
+torch.manual_seed(r)
+with torch.no_grad():
+    for p in m.parameters():
+        p.normal_()
+be.apply_ddp(m)
+w = m.weight.detach().clone()
+g = [torch.zeros_like(w) for _ in range(2)]
+dist.all_gather(g, w)
+assert torch.equal(g[0], g[1]), "replicas must start identical"
+flat = torch.full((1000,), float(r + 1))
+allreduce_flat_grads(flat, chunk_bytes=1024)
+assert torch.allclose(flat, torch.full((1000,), 1.5))
+mt = fused_step_metrics(torch.tensor(2.0 * (r + 1)), torch.tensor(float(r)))
+assert abs(mt["train/grad_norm"] - 3.0) < 1e-6 and abs(mt["train/global_avg_loss"] - 0.5) < 1e-6 and mt["train/global_max_loss"] == 1.0
+assert dist_mean(torch.tensor([float(r)])) == 0.5 and dist_max(torch.tensor([float(r)])) == 1.0
+be.wait_for_everyone()
+be.destroy()
+print("WORKER_OK", r)
+'''
+
+
+def test_parallel_backend_world2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, B2D_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)], env=env,
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("WORKER_OK") == 2
