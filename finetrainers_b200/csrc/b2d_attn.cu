@@ -535,6 +535,7 @@ using namespace b2d;
 
 extern "C" int b2d_attn_fwd(const void* q, const void* k, const void* v, const float* key_bias, void* out, float* lse,
                             int32_t B, int32_t H, int32_t Sq, int32_t Sk, float scale, void* stream) {
+    B2D_BIND(q);
     if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) return set_error(B2D_ERR_SHAPE, "attn_fwd: bad dims");
     AttnFwdParams p;
     memset(&p, 0, sizeof(p));
@@ -557,6 +558,7 @@ extern "C" int b2d_attn_fwd(const void* q, const void* k, const void* v, const f
 extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const float* key_bias, const void* out,
                             const void* dout, const float* lse, float* delta_ws, void* dq, void* dk, void* dv,
                             int32_t B, int32_t H, int32_t Sq, int32_t Sk, float scale, void* stream) {
+    B2D_BIND(q);
     if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) return set_error(B2D_ERR_SHAPE, "attn_bwd: bad dims");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     {

@@ -514,6 +514,7 @@ static int check_rowop(int rows, int D, int rps) {
 extern "C" int b2d_norm_modulate_fwd(const void* x, void* y, const void* shift_tab, const void* shift_emb,
                                      const void* scale_tab, const void* scale_emb, int64_t emb_stride, int32_t rows,
                                      int32_t D, int32_t rows_per_sample, float eps, int32_t layer_norm, void* stream) {
+    B2D_BIND(x);
     if (int rc = check_rowop(rows, D, rows_per_sample)) return rc;
     norm_modulate_fwd_kernel<<<rows, ROW_THREADS, 0, STREAM>>>(
         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)shift_tab, (const __nv_bfloat16*)shift_emb,
@@ -526,6 +527,7 @@ extern "C" int b2d_norm_modulate_bwd(const void* dy, const void* x, const void* 
                                      const void* scale_tab, const void* scale_emb, const void* gate2_tab,
                                      const void* gate2_emb, void* out2, int64_t emb_stride, int32_t rows, int32_t D,
                                      int32_t rows_per_sample, float eps, int32_t layer_norm, void* stream) {
+    B2D_BIND(dy);
     if (int rc = check_rowop(rows, D, rows_per_sample)) return rc;
     norm_modulate_bwd_kernel<<<rows, ROW_THREADS, 0, STREAM>>>(
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dx_in, (__nv_bfloat16*)dx_out,
@@ -537,6 +539,7 @@ extern "C" int b2d_norm_modulate_bwd(const void* dy, const void* x, const void* 
 
 extern "C" int b2d_colscale(const void* x, void* out, const void* tab, const void* emb, int64_t emb_stride,
                             int32_t rows, int32_t D, int32_t rows_per_sample, void* stream) {
+    B2D_BIND(x);
     if (D % 8) return set_error(B2D_ERR_SHAPE, "colscale: D %% 8");
     long long total8 = (long long)rows * D / 8;
     colscale_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, STREAM>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out,
@@ -550,6 +553,7 @@ extern "C" int b2d_colscale(const void* x, void* out, const void* tab, const voi
 extern "C" int b2d_qknorm_rope_fwd(const void* src, int64_t ld, int64_t col_off, const void* weight, const void* cos,
                                    const void* sin, void* dst, int32_t B, int32_t S, int32_t H, int32_t norm,
                                    float eps, void* stream) {
+    B2D_BIND(src);
     if (int rc = check_rowop(B * S, H * 64, S)) return rc;
     if ((ld % 8) || (col_off % 8)) return set_error(B2D_ERR_ALIGN, "qknorm_rope: ld/col_off must be multiples of 8");
     qknorm_rope_fwd_kernel<<<B * S, ROW_THREADS, 0, STREAM>>>((const __nv_bfloat16*)src, ld, col_off,
@@ -563,6 +567,7 @@ extern "C" int b2d_qknorm_rope_bwd(const void* dsrc_heads, const void* x, int64_
                                    const void* weight, const void* cos, const void* sin, void* dx, int64_t ld_dx,
                                    int64_t dx_col_off, int32_t B, int32_t S, int32_t H, int32_t norm, float eps,
                                    void* stream) {
+    B2D_BIND(dsrc_heads);
     if (int rc = check_rowop(B * S, H * 64, S)) return rc;
     if ((ld % 8) || (col_off % 8) || (ld_dx % 8) || (dx_col_off % 8))
         return set_error(B2D_ERR_ALIGN, "qknorm_rope_bwd: ld/col_off must be multiples of 8");
@@ -575,6 +580,7 @@ extern "C" int b2d_qknorm_rope_bwd(const void* dsrc_heads, const void* x, int64_
 
 extern "C" int b2d_rope_table(float* cos, float* sin, int32_t F, int32_t H, int32_t W, int32_t D, float sf, float sh,
                               float sw, void* stream) {
+    B2D_BIND(cos);
     if (D % 2 || D / 6 < 2) return set_error(B2D_ERR_SHAPE, "rope_table: D must be even and >= 12");
     long long n = (long long)F * H * W * (D / 2);
     rope_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(cos, sin, F, H, W, D, sf, sh, sw);
@@ -585,6 +591,7 @@ extern "C" int b2d_rope_table(float* cos, float* sin, int32_t F, int32_t H, int3
 extern "C" int b2d_prep_noise_pack(const void* latents, const void* noise, const float* mean, const float* std,
                                    const float* sigma, const float* sigma_ff, void* x_t, void* target, int32_t B,
                                    int32_t C, int32_t F, int32_t HW, void* stream) {
+    B2D_BIND(latents);
     long long n = (long long)B * C * F * HW;
     if (n <= 0) return set_error(B2D_ERR_SHAPE, "prep: empty");
     prep_noise_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(
@@ -599,6 +606,7 @@ constexpr int REDUCE_BLOCKS = 296;
 extern "C" int b2d_loss_mse(const void* pred, const void* target, const float* weight, float loss_scale,
                             float* loss_out, void* dpred, float* partial_ws, int32_t B, int64_t per_sample,
                             void* stream) {
+    B2D_BIND(pred);
     if (per_sample % 8) return set_error(B2D_ERR_SHAPE, "loss: per_sample %% 8");
     loss_mse_kernel<<<REDUCE_BLOCKS, ROW_THREADS, 0, STREAM>>>((const __nv_bfloat16*)pred, (const __nv_bfloat16*)target,
                                                                weight, loss_scale, (__nv_bfloat16*)dpred, partial_ws, B,
@@ -610,12 +618,14 @@ extern "C" int b2d_loss_mse(const void* pred, const void* target, const float* w
 }
 
 extern "C" int b2d_timestep_sinusoid(const float* t, void* out, int32_t n, void* stream) {
+    B2D_BIND(t);
     timestep_sinusoid_kernel<<<(n * 128 + 255) / 256, 256, 0, STREAM>>>(t, (__nv_bfloat16*)out, n);
     B2D_CHECK_LAUNCH("timestep_sinusoid");
     return 0;
 }
 
 extern "C" int b2d_cast_f32_bf16(const float* src, void* dst, int64_t n, float scale, void* stream) {
+    B2D_BIND(src);
     if (n <= 0) return 0;
     long long n4 = (n + 3) / 4;
     cast_f32_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, STREAM>>>(src, (__nv_bfloat16*)dst, n, scale);
@@ -624,6 +634,7 @@ extern "C" int b2d_cast_f32_bf16(const float* src, void* dst, int64_t n, float s
 }
 
 extern "C" int b2d_sumsq(const float* x, int64_t n, float* out_sumsq, float* partial_ws, void* stream) {
+    B2D_BIND(x);
     sumsq_kernel<<<REDUCE_BLOCKS, ROW_THREADS, 0, STREAM>>>(x, n, partial_ws);
     B2D_CHECK_LAUNCH("sumsq");
     final_sum_kernel<<<1, ROW_THREADS, 0, STREAM>>>(partial_ws, REDUCE_BLOCKS, out_sumsq, 1);
@@ -634,6 +645,7 @@ extern "C" int b2d_sumsq(const float* x, int64_t n, float* out_sumsq, float* par
 extern "C" int b2d_adamw_clip(float* p, float* g, float* m, float* v, int64_t n, const float* sumsq, float max_norm,
                               float lr, float beta1, float beta2, float eps, float wd, int32_t step, float grad_div,
                               void* stream) {
+    B2D_BIND(p);
     if (n <= 0) return 0;
     float bc1 = 1.f - powf(beta1, (float)step);
     float bc2s = sqrtf(1.f - powf(beta2, (float)step));

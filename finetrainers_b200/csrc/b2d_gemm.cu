@@ -442,6 +442,8 @@ using namespace b2d;
 extern "C" int b2d_gemm(const b2d_gemm_desc* d, void* stream_v) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     if (d == nullptr) return set_error(B2D_ERR_ARG, "gemm: null descriptor");
+    if (d->A == nullptr || d->B == nullptr || d->out == nullptr) return set_error(B2D_ERR_ARG, "gemm: null operand");
+    B2D_BIND(d->A);
     if (d->M <= 0 || d->N <= 0 || d->K <= 0) return set_error(B2D_ERR_SHAPE, "gemm: M,N,K must be positive");
     if (d->N % 8 != 0) return set_error(B2D_ERR_SHAPE, "gemm: N %% 8 != 0 (N=%d)", d->N);
     if (d->K2 % 64 != 0) return set_error(B2D_ERR_SHAPE, "gemm: K2 %% 64 != 0");

@@ -12,6 +12,13 @@ namespace b2d {
 // printf-style; stores a thread-local message and returns `code`.
 int set_error(int code, const char* fmt, ...);
 
+// bind the calling host thread to the device owning `device_ptr` (first call per thread); see b2d_runtime.cu
+int bind_thread(const void* device_ptr);
+#define B2D_BIND(ptr)                                  \
+    do {                                               \
+        if (int rc__ = b2d::bind_thread(ptr)) return rc__; \
+    } while (0)
+
 // number of SMs of the current device (cached per device); <=0 on error
 int device_sm_count();
 

@@ -18,6 +18,24 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 
+// The library links its own (static) CUDA runtime, whose per-thread "current device" is independent of the caller's
+// (PyTorch's) runtime.  Autograd runs backward on a fresh host thread, so every entry point binds the calling thread to
+// the device that owns the buffers it was handed (once per thread).
+int bind_thread(const void* device_ptr) {
+    static thread_local int bound = -1;
+    if (bound >= 0) return B2D_OK;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, device_ptr);
+    if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "cudaPointerGetAttributes: %s", cudaGetErrorString(e));
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)
+        return set_error(B2D_ERR_ARG, "libb2d needs device pointers (got host/unregistered memory): no CPU fallback");
+    e = cudaSetDevice(at.device);
+    if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "cudaSetDevice(%d): %s", at.device, cudaGetErrorString(e));
+    cudaFree(0);  // make the primary context current for driver-API calls (cuTensorMapEncodeTiled)
+    bound = at.device;
+    return B2D_OK;
+}
+
 int device_sm_count() {
     static int cache[64] = {};
     int dev = 0;

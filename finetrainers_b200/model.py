@@ -408,7 +408,7 @@ class B200LTXTransformer(nn.Module):
         if lora is not None:
             Ab, Bb, u, n_ad = lora
             rp = self.rpad
-            ops.gemm(x, Ab, u, M=M, N=n_ad * rp, K=K, alpha=self.lora_scaling)
+            ops.gemm(x, Ab, u, M=M, N=n_ad * rp, K=K, alpha=self.lora_scaling, tag="lora_u")
             ops.gemm(x, W, out, M=M, N=N, K=K, bias=bias, A2=u, B2=Bb, K2=rp, a2_group_n=(N // n_ad if n_ad > 1 else 0),
                      **kw)
         else:
@@ -483,7 +483,7 @@ class B200LTXTransformer(nn.Module):
             ops.norm_modulate_fwd(h2, ws["n2"], sst[3], temb[:, 3 * d:], sst[4], temb[:, 4 * d:], 6 * d, R, d, S,
                                   cfg.norm_eps)
             ops.gemm(ws["n2"], e["W1"], ws["f"], M=R, N=cfg.ffn_mult * d, K=d, bias=e["b1"], epi=ops.EPI_GELU,
-                     out2=ws["ffpre"][l])
+                     out2=ws["ffpre"][l], tag="ffn_up")
             ops.gemm(ws["f"], e["W2"], ws["h"][l + 1], M=R, N=d, K=cfg.ffn_mult * d, bias=e["b2"], epi=ops.EPI_GATE_RES,
                      res=h2, gate_table=sst[5], gate_temb=temb[:, 5 * d:], temb_stride=6 * d, rows_per_sample=S)
         # K13: final LayerNorm + modulate (table rows 0 = shift, 1 = scale; embedded_timestep), proj_out
@@ -509,14 +509,14 @@ class B200LTXTransformer(nn.Module):
         du = du.view(-1)[:M * n_ad * rp].view(M, n_ad * rp)
         # du_j = s * dy_j B_j
         ops.gemm(dy, e["Bb_" + g], du, M=M, N=rp, K=Nj, b_mn=True, batch=n_ad, a_boff=(0, Nj), b_boff=(Nj, 0),
-                 c_boff=rp, ldc=n_ad * rp, alpha=self.lora_scaling)
+                 c_boff=rp, ldc=n_ad * rp, alpha=self.lora_scaling, tag="lora_du")
         # dB_j += dy_j^T u_j
         ops.gemm(dy, u, e["gB_" + g], M=Nj, N=rp, K=M, a_mn=True, b_mn=True, batch=n_ad, a_boff=(0, Nj), b_boff=(0, rp),
-                 c_boff=Nj * rp, ldc=rp, epi=ops.EPI_F32_ATOMIC, block_n=64 if rp == 64 else 128,
+                 c_boff=Nj * rp, ldc=rp, epi=ops.EPI_F32_ATOMIC, block_n=64 if rp == 64 else 128, tag="lora_dB",
                  splits=self._splits(-(-Nj // 128) * n_ad * (rp // (64 if rp == 64 else 128)), kb))
         # dA += du^T x   (computed as (x^T du)^T)
         ops.gemm(x, du, e["gA_" + g], M=K, N=n_ad * rp, K=M, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC_T, ldc=K,
-                 block_n=64, splits=self._splits(-(-K // 128) * (n_ad * rp // 64), kb))
+                 block_n=64, tag="lora_dA", splits=self._splits(-(-K // 128) * (n_ad * rp // 64), kb))
         return du
 
     def _backward_impl(self, dpred):

@@ -13,7 +13,32 @@ from .lib import GemmDesc, check
 
 EPI_STORE, EPI_GELU, EPI_SILU, EPI_GATE_RES, EPI_MUL_DGELU, EPI_F32_ATOMIC, EPI_F32_ATOMIC_T, EPI_F32_STORE = range(8)
 
-LAUNCH_COUNT = 0  # number of libb2d kernel-launching calls (bench.py reports it as gpu_launches)
+LAUNCH_COUNT = 0  # number of libb2d kernels launched (bench.py reports it as gpu_launches)
+TIMING = False    # when True every wrapper brackets its launch with CUDA events on the current stream
+KERNEL_TIMES = {}  # tag -> [(start_event, end_event), ...]
+
+
+class _Timed:
+    __slots__ = ("tag", "e0")
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if TIMING:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if TIMING:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            KERNEL_TIMES.setdefault(self.tag, []).append((self.e0, e1))
+
+
+def collect_kernel_times():
+    """{tag: (total_ms, launches)} — call after torch.cuda.synchronize()."""
+    return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in KERNEL_TIMES.items()}
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -37,7 +62,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          a_mn=False, b_mn=False, A2=None, B2=None, K2=0, lda2=None, ldb2=None, a2_group_n=0, splits=1, batch=1,
          a_boff=(0, 0), b_boff=(0, 0), c_boff=0, epi=EPI_STORE, alpha=1.0, out2=None, ldc2=None, bias=None, res=None,
          ldres=None, aux=None, ldaux=None, gate_table=None, gate_temb=None, gate2_table=None, gate2_temb=None,
-         temb_stride=0, rows_per_sample=0, block_n=0, max_ctas=0):
+         temb_stride=0, rows_per_sample=0, block_n=0, max_ctas=0, tag="gemm"):
     """C = epilogue(alpha * (opA(A) opB(B)^T + A2 B2^T)).  See include/b2d.h b2d_gemm_desc."""
     d = GemmDesc()
     d.A = A.data_ptr(); d.lda = lda if lda is not None else A.stride(0)
@@ -71,49 +96,55 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     d.rows_per_sample = rows_per_sample
     d.block_n = block_n
     d.max_ctas = max_ctas
-    check(_l.load().b2d_gemm(C.byref(d), _stream()), "gemm")
+    with _Timed(tag):
+        check(_l.load().b2d_gemm(C.byref(d), _stream()), "gemm")
     _count()
     return out
 
 
 def norm_modulate_fwd(x, y, shift_tab, shift_emb, scale_tab, scale_emb, emb_stride, rows, D, rows_per_sample, eps,
                       layer_norm=False):
-    check(_l.load().b2d_norm_modulate_fwd(_ptr(x), _ptr(y), _ptr(shift_tab), _ptr(shift_emb), _ptr(scale_tab),
-                                          _ptr(scale_emb), C.c_int64(emb_stride), rows, D, rows_per_sample,
-                                          C.c_float(eps), int(layer_norm), _stream()), "norm_modulate_fwd")
+    with _Timed("norm_modulate_fwd"):
+        check(_l.load().b2d_norm_modulate_fwd(_ptr(x), _ptr(y), _ptr(shift_tab), _ptr(shift_emb), _ptr(scale_tab),
+                                              _ptr(scale_emb), C.c_int64(emb_stride), rows, D, rows_per_sample,
+                                              C.c_float(eps), int(layer_norm), _stream()), "norm_modulate_fwd")
     _count()
     return y
 
 
 def norm_modulate_bwd(dy, x, dx_in, dx_out, scale_tab, scale_emb, emb_stride, rows, D, rows_per_sample, eps,
                       layer_norm=False, gate2_tab=None, gate2_emb=None, out2=None):
-    check(_l.load().b2d_norm_modulate_bwd(_ptr(dy), _ptr(x), _ptr(dx_in), _ptr(dx_out), _ptr(scale_tab),
-                                          _ptr(scale_emb), _ptr(gate2_tab), _ptr(gate2_emb), _ptr(out2),
-                                          C.c_int64(emb_stride), rows, D, rows_per_sample, C.c_float(eps),
-                                          int(layer_norm), _stream()), "norm_modulate_bwd")
+    with _Timed("norm_modulate_bwd"):
+        check(_l.load().b2d_norm_modulate_bwd(_ptr(dy), _ptr(x), _ptr(dx_in), _ptr(dx_out), _ptr(scale_tab),
+                                              _ptr(scale_emb), _ptr(gate2_tab), _ptr(gate2_emb), _ptr(out2),
+                                              C.c_int64(emb_stride), rows, D, rows_per_sample, C.c_float(eps),
+                                              int(layer_norm), _stream()), "norm_modulate_bwd")
     _count()
     return dx_out
 
 
 def colscale(x, out, tab, emb, emb_stride, rows, D, rows_per_sample):
-    check(_l.load().b2d_colscale(_ptr(x), _ptr(out), _ptr(tab), _ptr(emb), C.c_int64(emb_stride), rows, D,
-                                 rows_per_sample, _stream()), "colscale")
+    with _Timed("colscale"):
+        check(_l.load().b2d_colscale(_ptr(x), _ptr(out), _ptr(tab), _ptr(emb), C.c_int64(emb_stride), rows, D,
+                                     rows_per_sample, _stream()), "colscale")
     _count()
     return out
 
 
 def qknorm_rope_fwd(src, ld, col_off, weight, cos, sin, dst, B, S, H, norm, eps):
-    check(_l.load().b2d_qknorm_rope_fwd(_ptr(src), C.c_int64(ld), C.c_int64(col_off), _ptr(weight), _ptr(cos),
-                                        _ptr(sin), _ptr(dst), B, S, H, int(norm), C.c_float(eps), _stream()),
-          "qknorm_rope_fwd")
+    with _Timed("qknorm_rope_fwd"):
+        check(_l.load().b2d_qknorm_rope_fwd(_ptr(src), C.c_int64(ld), C.c_int64(col_off), _ptr(weight), _ptr(cos),
+                                            _ptr(sin), _ptr(dst), B, S, H, int(norm), C.c_float(eps), _stream()),
+              "qknorm_rope_fwd")
     _count()
     return dst
 
 
 def qknorm_rope_bwd(dyh, x, ld, col_off, weight, cos, sin, dx, ld_dx, dx_col_off, B, S, H, norm, eps):
-    check(_l.load().b2d_qknorm_rope_bwd(_ptr(dyh), _ptr(x), C.c_int64(ld), C.c_int64(col_off), _ptr(weight), _ptr(cos),
-                                        _ptr(sin), _ptr(dx), C.c_int64(ld_dx), C.c_int64(dx_col_off), B, S, H,
-                                        int(norm), C.c_float(eps), _stream()), "qknorm_rope_bwd")
+    with _Timed("qknorm_rope_bwd"):
+        check(_l.load().b2d_qknorm_rope_bwd(_ptr(dyh), _ptr(x), C.c_int64(ld), C.c_int64(col_off), _ptr(weight),
+                                            _ptr(cos), _ptr(sin), _ptr(dx), C.c_int64(ld_dx), C.c_int64(dx_col_off), B,
+                                            S, H, int(norm), C.c_float(eps), _stream()), "qknorm_rope_bwd")
     _count()
     return dx
 
@@ -125,16 +156,18 @@ def rope_table(cos, sin, F, H, W, D, sf, sh, sw):
 
 
 def attn_fwd(q, k, v, key_bias, out, lse, B, H, Sq, Sk, scale):
-    check(_l.load().b2d_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(key_bias), _ptr(out), _ptr(lse), B, H, Sq, Sk,
-                                 C.c_float(scale), _stream()), "attn_fwd")
+    with _Timed("attn_fwd"):
+        check(_l.load().b2d_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(key_bias), _ptr(out), _ptr(lse), B, H, Sq, Sk,
+                                     C.c_float(scale), _stream()), "attn_fwd")
     _count()
     return out
 
 
 def attn_bwd(q, k, v, key_bias, out, dout, lse, delta_ws, dq, dk, dv, B, H, Sq, Sk, scale):
-    check(_l.load().b2d_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(key_bias), _ptr(out), _ptr(dout), _ptr(lse),
-                                 _ptr(delta_ws), _ptr(dq), _ptr(dk), _ptr(dv), B, H, Sq, Sk, C.c_float(scale),
-                                 _stream()), "attn_bwd")
+    with _Timed("attn_bwd"):
+        check(_l.load().b2d_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(key_bias), _ptr(out), _ptr(dout), _ptr(lse),
+                                     _ptr(delta_ws), _ptr(dq), _ptr(dk), _ptr(dv), B, H, Sq, Sk, C.c_float(scale),
+                                     _stream()), "attn_bwd")
     _count(3)
 
 
@@ -145,8 +178,9 @@ def prep_noise_pack(latents, noise, mean, std, sigma, sigma_ff, x_t, target, B, 
 
 
 def loss_mse(pred, target, weight, loss_scale, loss_out, dpred, partial_ws, B, per_sample):
-    check(_l.load().b2d_loss_mse(_ptr(pred), _ptr(target), _ptr(weight), C.c_float(loss_scale), _ptr(loss_out),
-                                 _ptr(dpred), _ptr(partial_ws), B, C.c_int64(per_sample), _stream()), "loss_mse")
+    with _Timed("loss"):
+        check(_l.load().b2d_loss_mse(_ptr(pred), _ptr(target), _ptr(weight), C.c_float(loss_scale), _ptr(loss_out),
+                                     _ptr(dpred), _ptr(partial_ws), B, C.c_int64(per_sample), _stream()), "loss_mse")
     _count(2)
 
 
@@ -156,17 +190,20 @@ def timestep_sinusoid(t, out, n):
 
 
 def cast_f32_bf16(src, dst, n, scale=1.0):
-    check(_l.load().b2d_cast_f32_bf16(_ptr(src), _ptr(dst), C.c_int64(n), C.c_float(scale), _stream()), "cast")
+    with _Timed("cast"):
+        check(_l.load().b2d_cast_f32_bf16(_ptr(src), _ptr(dst), C.c_int64(n), C.c_float(scale), _stream()), "cast")
     _count()
 
 
 def sumsq(x, n, out, partial_ws):
-    check(_l.load().b2d_sumsq(_ptr(x), C.c_int64(n), _ptr(out), _ptr(partial_ws), _stream()), "sumsq")
+    with _Timed("sumsq"):
+        check(_l.load().b2d_sumsq(_ptr(x), C.c_int64(n), _ptr(out), _ptr(partial_ws), _stream()), "sumsq")
     _count(2)
 
 
 def adamw_clip(p, g, m, v, n, sumsq_t, max_norm, lr, beta1, beta2, eps, wd, step, grad_div=1.0):
-    check(_l.load().b2d_adamw_clip(_ptr(p), _ptr(g), _ptr(m), _ptr(v), C.c_int64(n), _ptr(sumsq_t),
-                                   C.c_float(max_norm), C.c_float(lr), C.c_float(beta1), C.c_float(beta2),
-                                   C.c_float(eps), C.c_float(wd), int(step), C.c_float(grad_div), _stream()), "adamw")
+    with _Timed("adamw"):
+        check(_l.load().b2d_adamw_clip(_ptr(p), _ptr(g), _ptr(m), _ptr(v), C.c_int64(n), _ptr(sumsq_t),
+                                       C.c_float(max_norm), C.c_float(lr), C.c_float(beta1), C.c_float(beta2),
+                                       C.c_float(eps), C.c_float(wd), int(step), C.c_float(grad_div), _stream()), "adamw")
     _count()

@@ -1,0 +1,84 @@
+"""GPU: the attention kernel against the reference's own known-answer recipe
+(/root/reference/tests/models/attention_dispatch.py:41-149: q,k,v = randn[2,8,256,64] bf16, torch seed 0; forward vs
+math SDPA atol 5e-3; backward of output.mean() atol 1e-3), called through the provider hook, plus LTX shapes, ragged
+lengths and the masked cross-attention case."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _util import rnd, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _math_sdpa(q, k, v, mask=None):
+    with torch.nn.attention.sdpa_kernel(torch.nn.attention.SDPBackend.MATH):
+        return F.scaled_dot_product_attention(q, k, v, attn_mask=mask)
+
+
+def test_reference_attention_kat_through_provider_hook():
+    from finetrainers_b200.attention import attention_dispatch, attention_provider, AttentionProvider
+    torch.manual_seed(0)
+    q, k, v = (torch.randn(2, 8, 256, 64, device="cuda", dtype=torch.bfloat16) for _ in range(3))
+    ref = _math_sdpa(q, k, v)
+    with attention_provider(AttentionProvider.B200):
+        out = attention_dispatch(q, k, v)
+    assert out.shape == ref.shape
+    assert (out.float() - ref.float()).abs().max().item() < 5e-3
+    # backward recipe: output.mean().backward(), compare grads at atol 1e-3
+    grads = []
+    for fn in (lambda a, b, c: _math_sdpa(a, b, c), lambda a, b, c: attention_dispatch(a, b, c)):
+        qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
+        fn(qq, kk, vv).mean().backward()
+        grads.append((qq.grad, kk.grad, vv.grad))
+    for a, b in zip(*grads):
+        assert (a.float() - b.float()).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,bias", [(1, 32, 2688, 2688, False), (2, 4, 2688, 128, True), (1, 2, 200, 72, True),
+                                            (1, 2, 128, 128, False), (1, 3, 1, 1, False), (2, 2, 130, 257, True)])
+def test_attention_fwd_bwd_shapes(B, H, Sq, Sk, bias):
+    from finetrainers_b200 import ops
+    torch.manual_seed(0)
+    q, k, v = rnd(B, H, Sq, 64), rnd(B, H, Sk, 64), rnd(B, H, Sk, 64)
+    kb = None
+    if bias:
+        lens = torch.randint(1, Sk + 1, (B,), device="cuda")
+        kb = ((1 - (torch.arange(Sk, device="cuda")[None] < lens[:, None]).float()) * -10000.0).contiguous()
+    out = torch.zeros(B, Sq, H * 64, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, Sq, device="cuda")
+    ops.attn_fwd(q, k, v, kb, out, lse, B, H, Sq, Sk, 0.125)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    am = kb[:, None, None, :] if kb is not None else None
+    ref = _math_sdpa(qf, kf, vf, am)
+    assert rel_err(out, ref.transpose(1, 2).flatten(2)) < 1e-2
+    s = (qf @ kf.transpose(-1, -2)) * 0.125 + (am if am is not None else 0)
+    assert (lse - torch.logsumexp(s, -1)).abs().max().item() < 1e-3
+    dout = rnd(B, Sq, H * 64)
+    ref.backward(dout.float().unflatten(2, (H, 64)).transpose(1, 2))
+    dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+    ws = torch.zeros(B, H, Sq, device="cuda")
+    ops.attn_bwd(q, k, v, kb, out, dout, lse, ws, dq, dk, dv, B, H, Sq, Sk, 0.125)
+    assert rel_err(dq, qf.grad) < 2e-2 and rel_err(dk, kf.grad) < 2e-2 and rel_err(dv, vf.grad) < 2e-2
+
+
+def test_attention_properties_full_size():
+    """Size-independent properties at the BASELINE shape: softmax rows sum to one (V = 1 => O = 1) and permuting the
+    keys/values together leaves the output unchanged (up to bf16 accumulation order)."""
+    from finetrainers_b200 import ops
+    torch.manual_seed(1)
+    B, H, S = 1, 32, 2688
+    q, k = rnd(B, H, S, 64), rnd(B, H, S, 64)
+    ones = torch.ones(B, H, S, 64, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(B, S, H * 64, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, S, device="cuda")
+    ops.attn_fwd(q, k, ones, None, out, lse, B, H, S, S, 0.125)
+    assert (out.float() - 1.0).abs().max().item() < 1e-2
+    v = rnd(B, H, S, 64)
+    ops.attn_fwd(q, k, v, None, out, lse, B, H, S, S, 0.125)
+    perm = torch.randperm(S, device="cuda")
+    out2 = torch.zeros_like(out)
+    lse2 = torch.zeros_like(lse)
+    ops.attn_fwd(q, k[:, :, perm].contiguous(), v[:, :, perm].contiguous(), None, out2, lse2, B, H, S, S, 0.125)
+    assert (out.float() - out2.float()).abs().max().item() < 2e-2
+    assert (lse - lse2).abs().max().item() < 1e-3

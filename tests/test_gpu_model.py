@@ -1,0 +1,125 @@
+"""GPU: whole-step parity of the B200 DiT engine against the CPU oracle (restated reference; parity of the oracle
+itself to real diffusers is unpinned — see oracle/ltx_oracle.py header), through the ModelSpecification / SFT-step API.
+Tolerance from BASELINE.json north_star: per-step loss within 1e-3 relative."""
+import pytest
+import torch
+
+from _util import build_pair, run_b200_micro, SMALL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rank", [64, 16])
+def test_small_model_step_matches_oracle(rank):
+    O, om, bm = build_pair(SMALL, rank)
+    batch = O.make_synthetic_batch(om.cfg, 2, 2, 4, 9, text_len=24, seed=7)  # S = 72: ragged vs the 128-row tiles
+    loss_o, pred_o = O.oracle_step(om, {k: (v.float() if v.is_floating_point() else v) for k, v in batch.items()})
+    st, loss_b, pred_b = run_b200_micro(bm, batch)
+    assert abs(loss_b - loss_o.item()) / abs(loss_o.item()) < 1e-3
+    assert rel_err(pred_b, pred_o) < 3e-2
+    og = dict(om.named_parameters())
+    # Gradient tolerance: 5 % of the parameter's own gradient scale, floored at 2 % of the global gradient scale.
+    # The floor matters only for the cross-attention q/k adapters: with synthetic weights the text softmax is nearly
+    # uniform, dS = P*(dP - delta) cancels to ~1e-7 (1000x below every other gradient) and ANY bf16 implementation --
+    # including the bf16-typed oracle, i.e. what the reference computes -- carries O(1) relative noise there.
+    gmax = max(p.grad.abs().max().item() for n, p in om.named_parameters() if "lora_" in n)
+    for n, p in bm.named_parameters():
+        if "lora_" in n:
+            go = og[n].grad
+            e = (p.grad.float().cpu() - go).abs().max().item() / max(go.abs().max().item(), 2e-2 * gmax)
+            assert e < 5e-2, (n, e)
+    # optimizer step: matches torch AdamW + clip on the oracle's gradients
+    params = [p for n, p in om.named_parameters() if "lora_" in n]
+    O.clip_grad_norm_(params, 1.0)
+    opt = torch.optim.AdamW(params, lr=5e-5, betas=(0.9, 0.99), weight_decay=1e-4, eps=1e-8)
+    opt.step()
+    st.optimizer_step()
+    torch.cuda.synchronize()
+    for n, p in bm.named_parameters():
+        if "lora_" in n:
+            assert (p.detach().float().cpu() - og[n].detach()).abs().max().item() < 2e-4, n
+
+
+def test_small_model_through_finetrainers_style_loss():
+    """The path finetrainers' own trainer takes: pred from spec.forward, loss in torch, loss.backward()."""
+    from finetrainers_b200.specification import LTXVideoModelSpecification
+    O, om, bm = build_pair(SMALL, 64)
+    batch = O.make_synthetic_batch(om.cfg, 1, 2, 4, 8, text_len=16, seed=3)
+    loss_o, _ = O.oracle_step(om, {k: (v.float() if v.is_floating_point() else v) for k, v in batch.items()})
+    spec = LTXVideoModelSpecification(bm.cfg)
+    spec.first_frame_conditioning_p = 0.0
+    cond = {"encoder_hidden_states": batch["encoder_hidden_states"].cuda(), "encoder_attention_mask": batch["encoder_attention_mask"].cuda()}
+    lat = {"latents": batch["latents"].cuda(), "latents_mean": batch["latents_mean"].cuda(), "latents_std": batch["latents_std"].cuda()}
+    pred, target, sig = spec.forward(bm, cond, lat, batch["sigmas"].cuda(), noise=batch["noise"].cuda())
+    loss = (pred.float() - target.float()).pow(2).mean(list(range(1, 3))).mean()  # trainer.py:474-478
+    loss.backward()
+    assert abs(loss.item() - loss_o.item()) / loss_o.item() < 1e-3
+    og = dict(om.named_parameters())
+    n = "transformer_blocks.1.attn1.to_q.lora_B.default.weight"
+    g = dict(bm.named_parameters())[n].grad
+    assert rel_err(g.cpu(), og[n].grad) < 5e-2
+    assert "hidden_states" in lat and "latents" not in lat  # same dict mutation as the reference forward
+
+
+def test_zero_lora_b_is_identity_and_deterministic():
+    """Properties at the BASELINE width (D=2048, S=2688), 2 blocks: (a) B = 0 adapters change nothing (bitwise) versus
+    the model without adapters, (b) forward is bitwise deterministic, (c) dA == 0 exactly when B == 0."""
+    from finetrainers_b200.model import B200LTXTransformer, LTXConfig
+    from oracle import ltx_oracle as O
+    cfg = LTXConfig(num_layers=2)
+    torch.manual_seed(0)
+    base = B200LTXTransformer(cfg, torch.bfloat16, "cuda")
+    with torch.no_grad():
+        for n, p in base.named_parameters():
+            p.normal_(0, 0.02) if "norm_" not in n else p.fill_(1.0)
+    sd = {k: v.clone() for k, v in base.state_dict().items()}
+    base.prepare()
+    lora = B200LTXTransformer(cfg, torch.bfloat16, "cuda")
+    lora.load_state_dict(sd)
+    lora.add_adapter(64, 64)  # B initialised to zero (peft init_lora_weights=True)
+    lora.prepare()
+    batch = O.make_synthetic_batch(O.LTXConfig(num_layers=2), 1, 7, 16, 24, seed=11)
+    x = torch.randn(1, 2688, 128, device="cuda").bfloat16()
+    args = dict(encoder_hidden_states=batch["encoder_hidden_states"].cuda(), timestep=torch.tensor([500], device="cuda"),
+                encoder_attention_mask=batch["encoder_attention_mask"].cuda(), num_frames=7, height=16, width=24,
+                rope_interpolation_scale=[8 / 25, 32, 32])
+    with torch.no_grad():
+        p0 = base(x, **args)[0].clone()
+        p1 = lora(x, **args)[0].clone()
+        p2 = lora(x, **args)[0].clone()
+    assert torch.equal(p1, p2)
+    assert torch.equal(p0, p1)
+    out = lora(x, **args)[0]
+    out.backward(torch.randn_like(out))
+    torch.cuda.synchronize()
+    for n, p in lora.named_parameters():
+        if "lora_A" in n:
+            assert p.grad.abs().max().item() == 0.0, n
+        if "lora_B" in n:
+            assert p.grad.abs().max().item() > 0.0, n
+
+
+@pytest.mark.timeout(900)
+def test_full_size_forward_loss_matches_oracle():
+    """BASELINE config 2 (LTX-2B, 49x512x768 -> 2688 tokens, B=1, r=64): forward loss vs the fp32-math oracle on CPU."""
+    from oracle import ltx_oracle as O
+    from finetrainers_b200.model import B200LTXTransformer, LTXConfig
+    ocfg = O.LTXConfig()
+    om = O.LTXTransformerOracle(ocfg)
+    O.add_lora(om, 64, 64)
+    O.synthetic_init_(om, seed=0, lora_b_std=0.02)
+    with torch.no_grad():
+        for n, p in om.named_parameters():
+            if "lora_" not in n:
+                p.copy_(p.to(torch.bfloat16).float())
+    bm = B200LTXTransformer(LTXConfig(), torch.bfloat16, "cuda")
+    bm.add_adapter(64, 64)
+    bm.load_state_dict(om.state_dict(), strict=True)
+    bm.prepare()
+    batch = O.make_synthetic_batch(ocfg, 1, 7, 16, 24, seed=1234)
+    st, loss_b, pred_b = run_b200_micro(bm, batch)
+    with torch.no_grad():
+        loss_o, pred_o = O.oracle_step(om, {k: (v.float() if v.is_floating_point() else v) for k, v in batch.items()},
+                                       backward=False)
+    assert abs(loss_b - loss_o.item()) / abs(loss_o.item()) < 1e-3
+    assert rel_err(pred_b, pred_o) < 5e-2

@@ -406,11 +406,12 @@ def check_model():
         print(f"[{' ok ' if ok else 'FAIL'}] model small r={rank}: loss b200={loss_b:.6f} oracle={loss_o.item():.6f} rel={rel:.2e}")
         og = dict(om.named_parameters())
         worst = 0.0
+        gmax = max(p.grad.abs().max().item() for n, p in om.named_parameters() if "lora_" in n)
         for n, p in bm.named_parameters():
             if "lora_" in n:
                 g_o = og[n].grad
                 g_b = p.grad.float().cpu()
-                denom = g_o.abs().max().item() + 1e-12
+                denom = max(g_o.abs().max().item(), 2e-2 * gmax)
                 e = (g_b - g_o).abs().max().item() / denom
                 worst = max(worst, e)
                 if e > 5e-2:
