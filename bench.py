@@ -85,8 +85,9 @@ def cpu_reference_sample(layers=4, threads=None):
     blocks and scales by 28/layers (embeds/head are negligible).  Returns (tokens/s, seconds_per_full_step, cores)."""
     import torch
     from oracle import ltx_oracle as O
-    cores = threads or os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()  # torch's default honours the cgroup/affinity limits of the box
     cfg = O.LTXConfig(num_layers=layers)
     m = O.LTXTransformerOracle(cfg)
     O.add_lora(m, RANK_LORA, RANK_LORA)
@@ -162,7 +163,7 @@ def run_b200(args):
     model.prepare()
     if be is not None:
         be.apply_ddp(model)
-    step = SFTTrainStep(model, flow_weighting_scheme="logit_normal", seed=42 + rank)
+    step = SFTTrainStep(model, flow_weighting_scheme="logit_normal", seed=42 + rank, use_cuda_graph=not args.no_graph)
 
     # ---- synthetic data: a small pool of pinned host batches, plus one device-resident copy
     g = torch.Generator().manual_seed(1234 + rank)
@@ -211,22 +212,33 @@ def run_b200(args):
             ms = t.item()
         return ms
 
-    for i in range(max(args.warmup, 3)):
+    n_before = ops.LAUNCH_COUNT
+    step_resident(0)                       # eager: also counts the kernels one step launches
+    launches_per_step = ops.LAUNCH_COUNT - n_before
+    for i in range(max(args.warmup, 3) + 2):   # +2: eager warm-ups before the CUDA graph is captured
         step_resident(i)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    n0 = ops.LAUNCH_COUNT
     ms_total = timed(step_resident, args.steps)
-    launches = ops.LAUNCH_COUNT - n0
-    # instrumented pass (separate from the headline timing): CUDA events around every libb2d launch
-    ops.KERNEL_TIMES.clear()
-    ops.TIMING = True
-    n_inst = min(3, args.steps)
-    timed(step_resident, n_inst)
-    ops.TIMING = False
-    torch.cuda.synchronize()
-    ktimes = ops.collect_kernel_times()
+    launches = launches_per_step * args.steps
+    # dominant kernel measured live: the FFN up-projection GEMM launch of the step (2688 x 8192 x 2048, GELU epilogue,
+    # two outputs), CUDA events on the launching stream, operands rotated over 3 buffer sets (> 126 MB L2 in total)
+    R_, D_ = B * S_TOK, 2048
+    sets = [(torch.randn(R_, D_, device=dev).bfloat16(), torch.empty(R_, 4 * D_, device=dev, dtype=torch.bfloat16),
+             torch.empty(R_, 4 * D_, device=dev, dtype=torch.bfloat16)) for _ in range(3)]
+    e_blk = model._blk[0]
+
+    def ffn_up(i):
+        x_, f_, pre_ = sets[i % 3]
+        ops.gemm(x_, e_blk["W1"], f_, M=R_, N=4 * D_, K=D_, bias=e_blk["b1"], epi=ops.EPI_GELU, out2=pre_)
+
+    for i in range(3):
+        ffn_up(i)
+    n_k = 30
+    ms_k = timed(ffn_up, n_k)
+    ktimes = {"ffn_up": (ms_k, n_k)}
+    del sets
     for i in range(2):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
@@ -272,7 +284,7 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 12,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-        "kernel_ms_per_step": {k: round(v[0] / n_inst, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])},
+        "cuda_graph": not args.no_graph,
     }
     print(json.dumps(line))
     if be is not None:
@@ -287,6 +299,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 5:

@@ -155,20 +155,41 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
             mbar_wait(s_full, j & 1);
             tc_fence_after();
             const int kv0 = j * TILE;
-            // ---- pass 1: row max (log2 domain)
-            float mx = -INFINITY;
+            const bool fast = (kb == nullptr) && (kv0 + TILE <= p.Sk);  // full tile, no bias: no per-element masks
+            // ---- pass 1: row max (log2 domain); 4 independent accumulators keep the FMNMX chain short
+            float mx;
+            if (fast) {
+                float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld32(tS + lane_off + c * 32, v);
-                tmem_ld_wait();
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(tS + lane_off + hf * 64, v0);
+                    tmem_ld32(tS + lane_off + hf * 64 + 32, v1);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int col = kv0 + c * 32 + e;
-                    float x = __uint_as_float(v[e]) * p.scale_log2;
-                    if (kb) x += kb[min(col, p.Sk - 1)] * LOG2E;
-                    x = col < p.Sk ? x : -INFINITY;
-                    mx = fmaxf(mx, x);
+                    for (int e = 0; e < 32; e += 4) {
+                        m0 = fmaxf(m0, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
+                        m1 = fmaxf(m1, fmaxf(__uint_as_float(v0[e + 1]), __uint_as_float(v1[e + 1])));
+                        m2 = fmaxf(m2, fmaxf(__uint_as_float(v0[e + 2]), __uint_as_float(v1[e + 2])));
+                        m3 = fmaxf(m3, fmaxf(__uint_as_float(v0[e + 3]), __uint_as_float(v1[e + 3])));
+                    }
+                }
+                mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.scale_log2;  // scale > 0
+            } else {
+                mx = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tS + lane_off + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int col = kv0 + c * 32 + e;
+                        float x = __uint_as_float(v[e]) * p.scale_log2;
+                        if (kb) x += kb[min(col, p.Sk - 1)] * LOG2E;
+                        x = col < p.Sk ? x : -INFINITY;
+                        mx = fmaxf(mx, x);
+                    }
                 }
             }
             // ---- running max with lazy rescale of O
@@ -197,21 +218,34 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                 }
             }
             m_run = m_use;
-            // ---- pass 2: P = exp2(x - m), row sum, bf16 -> swizzled smem
+            // ---- pass 2: P = exp2(x - m), row sum (4 accumulators), bf16 -> swizzled smem
+            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
                 tmem_ld32(tS + lane_off + c * 32, v);
                 tmem_ld_wait();
                 float pv[32];
+                if (fast) {
+                    const float nm = -m_use;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int col = kv0 + c * 32 + e;
-                    float x = __uint_as_float(v[e]) * p.scale_log2 - m_use;
-                    if (kb) x += kb[min(col, p.Sk - 1)] * LOG2E;
-                    float pe = col < p.Sk ? fast_exp2(x) : 0.f;
-                    pv[e] = pe;
-                    l_run += pe;
+                    for (int e = 0; e < 32; e += 4) {
+                        pv[e] = fast_exp2(fmaf(__uint_as_float(v[e]), p.scale_log2, nm));
+                        pv[e + 1] = fast_exp2(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, nm));
+                        pv[e + 2] = fast_exp2(fmaf(__uint_as_float(v[e + 2]), p.scale_log2, nm));
+                        pv[e + 3] = fast_exp2(fmaf(__uint_as_float(v[e + 3]), p.scale_log2, nm));
+                        l0 += pv[e]; l1 += pv[e + 1]; l2 += pv[e + 2]; l3 += pv[e + 3];
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int col = kv0 + c * 32 + e;
+                        float x = __uint_as_float(v[e]) * p.scale_log2 - m_use;
+                        if (kb) x += kb[min(col, p.Sk - 1)] * LOG2E;
+                        float pe = col < p.Sk ? fast_exp2(x) : 0.f;
+                        pv[e] = pe;
+                        l0 += pe;
+                    }
                 }
                 uint8_t* chunk = sP + (c >> 1) * TILE_BYTES;
 #pragma unroll
@@ -221,6 +255,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                     *reinterpret_cast<uint4*>(chunk + sw128_off(r, (c & 1) * 4 + u)) = w;
                 }
             }
+            l_run += (l0 + l1) + (l2 + l3);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(p_full);
@@ -298,21 +333,29 @@ struct AttnBwdParams {
 };
 
 constexpr int BWD_Y_STAGES = 2;
-constexpr int BWD_SMEM = 2 * TILE_BYTES /*X1,X2*/ + BWD_Y_STAGES * 2 * TILE_BYTES /*Y1,Y2*/ + 4 * TILE_BYTES /*P, dS*/ +
-                         2 * 2 * TILE * 4 /*col vectors, double-buffered*/ + 1024 + 256;
+// TY = rows of the streamed (Y) tile per iteration.  TY = 64 keeps TMEM at 256 columns and smem under 100 KB so that two
+// CTAs share an SM and interleave their MMA and exp/elementwise phases.
+template <int TY>
+struct BwdCfg {
+    static constexpr int Y_BYTES = TY * HD * 2;           // one streamed tile  [TY x 64] bf16
+    static constexpr int PS_BYTES = TILE * TY * 2;        // P^T or dS^T       [128 x TY] bf16 (TY/64 swizzled chunks)
+    static constexpr int SMEM = 2 * TILE_BYTES + BWD_Y_STAGES * 2 * Y_BYTES + 2 * PS_BYTES + 2 * 2 * TY * 4 + 1024 + 256;
+    static constexpr int TMEM_COLS = (2 * TY + 128 <= 256) ? 256 : 512;
+};
 
-template <bool DKV>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+template <bool DKV, int TY>
+__global__ void __launch_bounds__(ATT_THREADS, (TY == 64 ? 2 : 1)) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+    using Cfg = BwdCfg<TY>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sX1 = smem;
     uint8_t* sX2 = sX1 + TILE_BYTES;
-    uint8_t* sY = sX2 + TILE_BYTES;                       // stage s: Y1 at +s*32K, Y2 at +16K
-    uint8_t* sP = sY + BWD_Y_STAGES * 2 * TILE_BYTES;     // 2 chunks  (P^T, DKV only)
-    uint8_t* sDS = sP + 2 * TILE_BYTES;                   // 2 chunks
-    float* sColA = reinterpret_cast<float*>(sDS + 2 * TILE_BYTES);  // [2][128]
-    float* sColD = sColA + 2 * TILE;                                 // [2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sColD + 2 * TILE);
+    uint8_t* sY = sX2 + TILE_BYTES;                          // stage s: Y1 at +s*2*Y_BYTES, Y2 right after
+    uint8_t* sP = sY + BWD_Y_STAGES * 2 * Cfg::Y_BYTES;      // P^T (DKV only)
+    uint8_t* sDS = sP + Cfg::PS_BYTES;
+    float* sColA = reinterpret_cast<float*>(sDS + Cfg::PS_BYTES);  // [2][TY]
+    float* sColD = sColA + 2 * TY;                                  // [2][TY]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sColD + 2 * TY);
     uint64_t* x_full = bars;
     uint64_t* y_full = bars + 1;   // [2]
     uint64_t* y_empty = bars + 3;  // [2]
@@ -327,7 +370,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     const int b = bh / p.H, h = bh % p.H;
     const int rowsX = DKV ? p.Sk : p.Sq;
     const int rowsY = DKV ? p.Sq : p.Sk;
-    const int n_y = (rowsY + TILE - 1) / TILE;
+    const int n_y = (rowsY + TY - 1) / TY;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmX1);
@@ -345,14 +388,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tS = tmem, tDP = tmem + 128, tO1 = tmem + 256, tO2 = tmem + 320;
+    const uint32_t tS = tmem, tDP = tmem + TY, tO1 = tmem + 2 * TY, tO2 = tmem + 2 * TY + 64;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -363,15 +406,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
             uint32_t phase = 0;
             for (int i = 0; i < n_y; ++i) {
                 mbar_wait(&y_empty[stage], phase ^ 1);
-                mbar_expect_tx(&y_full[stage], 2 * TILE_BYTES);
-                tma_load_4d(sY + stage * 2 * TILE_BYTES, &p.tmY1, &y_full[stage], 0, h, i * TILE, b);
-                tma_load_4d(sY + stage * 2 * TILE_BYTES + TILE_BYTES, &p.tmY2, &y_full[stage], 0, h, i * TILE, b);
+                mbar_expect_tx(&y_full[stage], 2 * Cfg::Y_BYTES);
+                tma_load_4d(sY + stage * 2 * Cfg::Y_BYTES, &p.tmY1, &y_full[stage], 0, h, i * TY, b);
+                tma_load_4d(sY + stage * 2 * Cfg::Y_BYTES + Cfg::Y_BYTES, &p.tmY2, &y_full[stage], 0, h, i * TY, b);
                 if (++stage == BWD_Y_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, TY, 0, 0);
             constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
             mbar_wait(x_full, 0);
             int stage = 0;
@@ -380,7 +423,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
             for (int i = 0; i < n_y; ++i) {
                 mbar_wait(&y_full[stage], phase);
                 tc_fence_after();
-                const uint32_t aY1 = smem_u32(sY + stage * 2 * TILE_BYTES), aY2 = aY1 + TILE_BYTES;
+                const uint32_t aY1 = smem_u32(sY + stage * 2 * Cfg::Y_BYTES), aY2 = aY1 + Cfg::Y_BYTES;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma_f16(tS, make_sdesc_sw128(aX1 + k * 32, 16, 1024), make_sdesc_sw128(aY1 + k * 32, 16, 1024),
@@ -394,12 +437,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
                 tc_fence_after();
                 if (DKV) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)  // out1 (dV) += P^T . dO_i   (Y2 as MN-major B)
+                    for (int k = 0; k < TY / 16; ++k)  // out1 (dV) += P^T . dO_i   (Y2 as MN-major B)
                         umma_f16(tO1, make_sdesc_sw128(aP + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
                                  make_sdesc_sw128(aY2 + k * 2048, 8192, 1024), idesc_o, (i > 0 || k > 0) ? 1u : 0u);
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k)  // out2 += dS . Y1   (Y1 as MN-major B)
+                for (int k = 0; k < TY / 16; ++k)  // out2 += dS . Y1   (Y1 as MN-major B)
                     umma_f16(tO2, make_sdesc_sw128(aDS + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
                              make_sdesc_sw128(aY1 + k * 2048, 8192, 1024), idesc_o, (i > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&y_empty[stage]);
@@ -426,10 +469,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
         if (!row_ok) rowA = -INFINITY;
         for (int i = 0; i < n_y; ++i) {
             // column vectors of this streamed tile (double-buffered by parity)
-            float* cA = sColA + (i & 1) * TILE;
-            float* cD = sColD + (i & 1) * TILE;
-            {
-                const int ycol = i * TILE + tid128;
+            float* cA = sColA + (i & 1) * TY;
+            float* cD = sColD + (i & 1) * TY;
+            if (tid128 < TY) {
+                const int ycol = i * TY + tid128;
                 const bool ok = ycol < rowsY;
                 if (DKV) {
                     cA[tid128] = ok ? -p.lse[bhoff * p.Sq + ycol] * LOG2E : -INFINITY;
@@ -448,7 +491,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
                 tc_fence_after();
             }
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < TY / 32; ++c) {
                 uint32_t sv[32], dv[32];
                 tmem_ld32(tS + lane_off + c * 32, sv);
                 tmem_ld32(tDP + lane_off + c * 32, dv);
@@ -457,7 +500,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
                     const int cc = c * 32 + e;
-                    float x = __uint_as_float(sv[e]) * p.scale_log2 + rowA + cA[cc];
+                    float x = fmaf(__uint_as_float(sv[e]), p.scale_log2, rowA + cA[cc]);
                     float pp = fast_exp2(x);
                     float dd = __uint_as_float(dv[e]) - (DKV ? cD[cc] : rowD);
                     pe[e] = pp;
@@ -509,23 +552,36 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem, 512);
+        tmem_dealloc(tmem, Cfg::TMEM_COLS);
     }
 }
 
 // 4-D map over a head-split view: dims (innermost first) [64, H, S, B]; strides in elements.
 static int make_head_map(CUtensorMap* m, const void* base, int B, int H, int S, long long stride_h, long long stride_s,
-                         long long stride_b) {
+                         long long stride_b, int box_rows = 128) {
     uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)S, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)stride_h * 2, (uint64_t)stride_s * 2, (uint64_t)stride_b * 2};
-    uint32_t box[4] = {64, 1, 128, 1};
+    uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
     return make_tmap_nd(m, base, 4, dims, strides, box, 2, 1);
 }
 
-template <typename K>
-static int set_smem(K kern, int bytes, const char* name) {
+// once per (kernel, device): keeps cudaFuncSetAttribute out of steady-state launches (and of CUDA-graph capture).
+// Keyed by the kernel's address (template instantiations share one function-pointer TYPE).
+static int set_smem(const void* kern, int bytes, const char* name) {
+    static const void* done_k[64];
+    static int done_dev[64];
+    static int n_done = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (int i = 0; i < n_done; ++i)
+        if (done_k[i] == kern && done_dev[i] == dev) return 0;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "cudaFuncSetAttribute(%s): %s", name, cudaGetErrorString(e));
+    if (n_done < 64) {
+        done_k[n_done] = kern;
+        done_dev[n_done] = dev;
+        ++n_done;
+    }
     return 0;
 }
 
@@ -548,7 +604,7 @@ extern "C" int b2d_attn_fwd(const void* q, const void* k, const void* v, const f
     p.lse = lse;
     p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
     p.scale_log2 = scale * LOG2E;
-    if ((rc = set_smem(attn_fwd_kernel, FWD_SMEM, "attn_fwd"))) return rc;
+    if ((rc = set_smem((const void*)attn_fwd_kernel, FWD_SMEM, "attn_fwd"))) return rc;
     dim3 grid((Sq + TILE - 1) / TILE, B * H);
     attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     B2D_CHECK_LAUNCH("attn_fwd");
@@ -567,28 +623,33 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
                                                                            (const __nv_bfloat16*)dout, delta_ws, B, H, Sq);
         B2D_CHECK_LAUNCH("attn_delta");
     }
-    CUtensorMap mQ, mK, mV, mdO;
+    constexpr int TY = 64;
+    CUtensorMap mQ, mK, mV, mdO, mQy, mKy, mVy, mdOy;  // X role: 128-row boxes; Y role: TY-row boxes
     int rc;
     if ((rc = make_head_map(&mQ, q, B, H, Sq, (long long)Sq * 64, 64, (long long)H * Sq * 64))) return rc;
     if ((rc = make_head_map(&mK, k, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64))) return rc;
     if ((rc = make_head_map(&mV, v, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64))) return rc;
     if ((rc = make_head_map(&mdO, dout, B, H, Sq, 64, (long long)H * 64, (long long)Sq * H * 64))) return rc;
+    if ((rc = make_head_map(&mQy, q, B, H, Sq, (long long)Sq * 64, 64, (long long)H * Sq * 64, TY))) return rc;
+    if ((rc = make_head_map(&mKy, k, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64, TY))) return rc;
+    if ((rc = make_head_map(&mVy, v, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64, TY))) return rc;
+    if ((rc = make_head_map(&mdOy, dout, B, H, Sq, 64, (long long)H * 64, (long long)Sq * H * 64, TY))) return rc;
     AttnBwdParams p;
     memset(&p, 0, sizeof(p));
     p.key_bias = key_bias; p.lse = lse; p.delta = delta_ws;
     p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
     p.scale = scale; p.scale_log2 = scale * LOG2E;
     // dK, dV
-    p.tmX1 = mK; p.tmX2 = mV; p.tmY1 = mQ; p.tmY2 = mdO;
+    p.tmX1 = mK; p.tmX2 = mV; p.tmY1 = mQy; p.tmY2 = mdOy;
     p.out1 = (__nv_bfloat16*)dv; p.out2 = (__nv_bfloat16*)dk;
-    if ((rc = set_smem(attn_bwd_kernel<true>, BWD_SMEM, "attn_bwd_dkv"))) return rc;
-    attn_bwd_kernel<true><<<dim3((Sk + TILE - 1) / TILE, B * H), ATT_THREADS, BWD_SMEM, st>>>(p);
+    if ((rc = set_smem((const void*)attn_bwd_kernel<true, TY>, BwdCfg<TY>::SMEM, "attn_bwd_dkv"))) return rc;
+    attn_bwd_kernel<true, TY><<<dim3((Sk + TILE - 1) / TILE, B * H), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
     B2D_CHECK_LAUNCH("attn_bwd_dkv");
     // dQ
-    p.tmX1 = mQ; p.tmX2 = mdO; p.tmY1 = mK; p.tmY2 = mV;
+    p.tmX1 = mQ; p.tmX2 = mdO; p.tmY1 = mKy; p.tmY2 = mVy;
     p.out1 = nullptr; p.out2 = (__nv_bfloat16*)dq;
-    if ((rc = set_smem(attn_bwd_kernel<false>, BWD_SMEM, "attn_bwd_dq"))) return rc;
-    attn_bwd_kernel<false><<<dim3((Sq + TILE - 1) / TILE, B * H), ATT_THREADS, BWD_SMEM, st>>>(p);
+    if ((rc = set_smem((const void*)attn_bwd_kernel<false, TY>, BwdCfg<TY>::SMEM, "attn_bwd_dq"))) return rc;
+    attn_bwd_kernel<false, TY><<<dim3((Sq + TILE - 1) / TILE, B * H), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
     B2D_CHECK_LAUNCH("attn_bwd_dq");
     return 0;
 }

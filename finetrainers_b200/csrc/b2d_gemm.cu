@@ -408,21 +408,29 @@ static int launch_gemm(const GemmKParams& kp, int grid, cudaStream_t stream) {
 
 template <int BN>
 static int dispatch_major(const GemmKParams& kp, int a_mn, int b_mn, int grid, cudaStream_t s) {
+    if constexpr (BN % 64 != 0) {
+        if (a_mn) return launch_gemm<BN, 1, 0>(kp, grid, s);
+        return launch_gemm<BN, 0, 0>(kp, grid, s);
+    }
     if (!a_mn && !b_mn) return launch_gemm<BN, 0, 0>(kp, grid, s);
     if (!a_mn && b_mn) return launch_gemm<BN, 0, 1>(kp, grid, s);
     if (a_mn && b_mn) return launch_gemm<BN, 1, 1>(kp, grid, s);
     return launch_gemm<BN, 1, 0>(kp, grid, s);
 }
 
-static int pick_block_n(int M, int N, int nsm, int work_mult) {
-    // minimise (waves * tile cost) over the candidate tile widths; cost ~ BN + fixed overhead
-    const int cands[4] = {256, 192, 128, 64};
+static int pick_block_n(int M, int N, int nsm, int work_mult, int b_mn, int group_n) {
+    // minimise (waves * tile cost) over the candidate tile widths; cost ~ BN + fixed overhead.
+    // 160 exists to beat wave quantisation at N = 2048 (13 x 21 = 273 tiles on 2 x 148 slots); MN-major B tiles are
+    // built from 64-column TMA boxes, so they need BN % 64 == 0.
+    const int cands[5] = {256, 192, 160, 128, 64};
     int best = 128;
     double best_t = 1e30;
     int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 5; ++i) {
         int bn = cands[i];
-        if (bn > N && bn != 64 && (N % bn) != 0 && N < bn) continue;
+        if (b_mn && (bn % 64) != 0) continue;
+        if (group_n > 0 && (group_n % bn) != 0) continue;
+        if (bn > N && bn != 64) continue;
         int n_tiles = (N + bn - 1) / bn;
         long long tiles = (long long)m_tiles * n_tiles * work_mult;
         long long waves = (tiles + nsm - 1) / nsm;
@@ -464,8 +472,9 @@ extern "C" int b2d_gemm(const b2d_gemm_desc* d, void* stream_v) {
     int nsm = device_sm_count();
     if (nsm <= 0) return B2D_ERR_CUDA;
     int max_ctas = d->max_ctas > 0 ? d->max_ctas : nsm;
-    int bn = d->block_n > 0 ? d->block_n : pick_block_n(d->M, d->N, max_ctas, splits * batch);
-    if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return set_error(B2D_ERR_ARG, "gemm: bad block_n %d", bn);
+    int bn = d->block_n > 0 ? d->block_n : pick_block_n(d->M, d->N, max_ctas, splits * batch, d->b_mn_major, d->a2_group_n);
+    if (bn != 64 && bn != 128 && bn != 160 && bn != 192 && bn != 256) return set_error(B2D_ERR_ARG, "gemm: bad block_n %d", bn);
+    if (d->b_mn_major && (bn % 64)) return set_error(B2D_ERR_ARG, "gemm: MN-major B needs block_n %% 64 == 0");
     if (d->a2_group_n > 0 && (d->a2_group_n % bn) != 0)
         return set_error(B2D_ERR_ARG, "gemm: a2_group_n (%d) must be a multiple of block_n (%d)", d->a2_group_n, bn);
 
@@ -532,6 +541,7 @@ extern "C" int b2d_gemm(const b2d_gemm_desc* d, void* stream_v) {
     switch (bn) {
         case 64: return dispatch_major<64>(kp, d->a_mn_major, d->b_mn_major, grid, stream);
         case 128: return dispatch_major<128>(kp, d->a_mn_major, d->b_mn_major, grid, stream);
+        case 160: return dispatch_major<160>(kp, d->a_mn_major, d->b_mn_major, grid, stream);
         case 192: return dispatch_major<192>(kp, d->a_mn_major, d->b_mn_major, grid, stream);
         default: return dispatch_major<256>(kp, d->a_mn_major, d->b_mn_major, grid, stream);
     }

@@ -65,14 +65,20 @@ def expand_tensor_dims(t: torch.Tensor, ndim: int) -> torch.Tensor:
 
 class SFTTrainStep:
     """One optimizer step = ``gradient_accumulation_steps`` micro-steps of forward/loss/backward, then
-    all-reduce (DDP) + clip + AdamW on the flat LoRA buffers."""
+    all-reduce (DDP) + clip + AdamW on the flat LoRA buffers.
+
+    ``use_cuda_graph=True`` captures prologue + forward + loss + backward of a micro-step (≈1.6k kernel launches) into
+    one CUDA graph per input shape: the reference step is launch/host-bound at B=1, and so is any
+    per-kernel Python dispatch; replaying a graph removes the host from the critical path.  Inputs are copied into static
+    device buffers; sigma / noise / first-frame decisions are drawn outside the graph with the same torch calls as the
+    reference and handed over through those buffers."""
 
     def __init__(self, transformer: B200LTXTransformer, spec: Optional[LTXVideoModelSpecification] = None, *,
                  lr: float = 5e-5, beta1: float = 0.9, beta2: float = 0.99, weight_decay: float = 1e-4,
                  eps: float = 1e-8, max_grad_norm: float = 1.0, gradient_accumulation_steps: int = 1,
                  flow_weighting_scheme: str = "logit_normal", flow_logit_mean: float = 0.0,
                  flow_logit_std: float = 1.0, flow_mode_scale: float = 1.29, seed: int = 42,
-                 process_group=None):
+                 process_group=None, use_cuda_graph: bool = False):
         self.transformer = transformer
         self.spec = spec or LTXVideoModelSpecification(transformer.cfg)
         self.scheduler = FlowMatchSchedulerTable()
@@ -100,35 +106,111 @@ class SFTTrainStep:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if (
             torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
-        self._dpred = {}
+        self.use_cuda_graph = use_cuda_graph
+        self._static: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._eager_runs: Dict[tuple, int] = {}
 
-    # -- forward + loss + backward of one micro-batch (trainer.py:436-483)
+    # -- static buffers per input shape ---------------------------------------------------------------------------
+    def _buffers(self, B, C, Fr, Hh, Ww, L, Cc):
+        key = (B, C, Fr, Hh, Ww, L, Cc)
+        st = self._static.get(key)
+        if st is None:
+            dev = self.device
+            S = Fr * Hh * Ww
+            bf = dict(dtype=torch.bfloat16, device=dev)
+            st = {
+                "latents": torch.zeros(B, C, Fr, Hh, Ww, **bf), "noise": torch.zeros(B, C, Fr, Hh, Ww, **bf),
+                "mean": torch.zeros(B, C, dtype=torch.float32, device=dev),
+                "std": torch.ones(B, C, dtype=torch.float32, device=dev),
+                "ehs": torch.zeros(B, L, Cc, **bf), "mask": torch.ones(B, L, dtype=torch.float32, device=dev),
+                "sig": torch.zeros(B, dtype=torch.float32, device=dev),
+                "sig_ff": torch.zeros(B, dtype=torch.float32, device=dev),
+                "x_t": torch.zeros(B, S, C, **bf), "target": torch.zeros(B, S, C, **bf),
+                "dpred": torch.zeros(B, S, C, **bf),
+            }
+            self._static[key] = st
+        return key, st
+
+    def _body(self, key, st):
+        """prologue + forward + loss + backward on the static buffers (capturable: no host sync, no data-dependent
+        Python control flow)."""
+        B, C, Fr, Hh, Ww, L, Cc = key
+        tr = self.transformer
+        ops.prep_noise_pack(st["latents"], st["noise"], st["mean"], st["std"], st["sig"], st["sig_ff"], st["x_t"],
+                            st["target"], B, C, Fr, Hh * Ww)
+        tvals = (st["sig"] * 1000.0).long().to(torch.float32)                  # base_specification.py:320
+        key_bias = ((1.0 - st["mask"]) * -10000.0).contiguous()               # patch.py:55-57
+        weights = prepare_loss_weights(st["sig"], self.scheme).contiguous()   # trainer.py:463-470
+        lfr = self.spec.frame_rate / self.spec.temporal_compression_ratio
+        rope_scale = (1 / lfr, float(self.spec.vae_spatial_compression_ratio), float(self.spec.vae_spatial_compression_ratio))
+        pred = tr._forward_impl(st["x_t"], st["ehs"], tvals, key_bias, Fr, Hh, Ww, rope_scale)
+        ops.loss_mse(pred, st["target"], weights, 1.0 / self.grad_accum, self.loss_buf, st["dpred"], self.partial, B,
+                     pred.shape[1] * pred.shape[2])
+        tr._backward_impl(st["dpred"])
+        self.loss_acc += self.loss_buf
+
+    # -- forward + loss + backward of one micro-batch (trainer.py:436-483) ---------------------------------------
+    @torch.no_grad()
     def micro_step(self, condition_model_conditions: Dict[str, torch.Tensor],
                    latent_model_conditions: Dict[str, torch.Tensor], sigmas: Optional[torch.Tensor] = None,
                    noise: Optional[torch.Tensor] = None) -> torch.Tensor:
-        B = latent_model_conditions["latents"].shape[0]
+        import random as _random
+        latents = latent_model_conditions["latents"]
+        B, C, Fr, Hh, Ww = latents.shape
+        ehs = condition_model_conditions["encoder_hidden_states"]
+        mask = condition_model_conditions.get("encoder_attention_mask")
+        key, st = self._buffers(B, C, Fr, Hh, Ww, ehs.shape[1], ehs.shape[2])
+        if not self.transformer._prepared:
+            self.transformer.prepare()
+        # ---- host-side sampling, identical calls to the reference (utils/diffusion.py:84-114, base_specification.py:296-305)
         if sigmas is None:
             sigmas = prepare_sigmas(self.scheduler, self.scheduler_sigmas, B, self.scheduler.config.num_train_timesteps,
                                     self.scheme, self.flow_logit_mean, self.flow_logit_std, self.flow_mode_scale,
                                     self.device, self.generator)
-        sigmas = expand_tensor_dims(sigmas, latent_model_conditions["latents"].ndim)
-        pred, target, sig_tok = self.spec.forward(self.transformer, condition_model_conditions,
-                                                  latent_model_conditions, sigmas, generator=self.generator,
-                                                  noise=noise)
-        weights = prepare_loss_weights(sig_tok[:, 0, 0].float(), self.scheme).contiguous()
-        key = tuple(pred.shape)
-        dpred = self._dpred.get(key)
-        if dpred is None:
-            dpred = torch.empty(pred.shape, dtype=torch.bfloat16, device=pred.device)
-            self._dpred[key] = dpred
-        per_sample = pred.shape[1] * pred.shape[2]
-        ops.loss_mse(pred, target, weights, 1.0 / self.grad_accum, self.loss_buf, dpred, self.partial, B, per_sample)
-        pred.backward(dpred)
-        self.loss_acc += self.loss_buf
+        st["sig"].copy_(sigmas.reshape(B), non_blocking=True)
+        st["latents"].copy_(latents, non_blocking=True)
+        if noise is None:
+            st["noise"].normal_(generator=self.generator)
+        else:
+            st["noise"].copy_(noise, non_blocking=True)
+        if "latents_mean" in latent_model_conditions:
+            st["mean"].copy_(latent_model_conditions["latents_mean"].reshape(B, C), non_blocking=True)
+            st["std"].copy_(latent_model_conditions["latents_std"].reshape(B, C), non_blocking=True)
+        st["ehs"].copy_(ehs, non_blocking=True)
+        if mask is not None:
+            st["mask"].copy_(mask, non_blocking=True)
+        else:
+            st["mask"].fill_(1.0)
+        if _random.random() < self.spec.first_frame_conditioning_p:
+            ff = torch.rand(B, device=self.device, generator=self.generator) * st["sig"]
+            st["sig_ff"].copy_(torch.clamp(ff, max=self.spec.min_first_frame_sigma))
+        else:
+            st["sig_ff"].copy_(st["sig"])  # first latent frame uses the same sigma: identical to the plain branch
+        # ---- the step body: eager, or one CUDA-graph replay
+        if not self.use_cuda_graph:
+            self._body(key, st)
+        else:
+            g = self._graphs.get(key)
+            if g is None:
+                n = self._eager_runs.get(key, 0)
+                if n < 2:  # warm-up eagerly (lazy one-time work: rope tables, func attributes, workspace allocation)
+                    self._body(key, st)
+                    self._eager_runs[key] = n + 1
+                else:
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._body(key, st)
+                    self._graphs[key] = g
+                    g.replay()
+            else:
+                g.replay()
         self.micro += 1
         return self.loss_buf
 
-    # -- clip + AdamW (+ DDP all-reduce) (trainer.py:486-520)
+    # -- clip + AdamW (+ DDP all-reduce) (trainer.py:486-520) ---------------------------------------------------
+    @torch.no_grad()
     def optimizer_step(self, sync_metrics: bool = False):
         tr = self.transformer
         g = tr.lora_grad_flat

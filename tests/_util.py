@@ -5,9 +5,10 @@ def rnd(*shape, scale=1.0, dtype=torch.bfloat16, device="cuda"):
     return (torch.randn(*shape, device=device) * scale).to(dtype)
 
 
-def rel_err(got, ref):
+def rel_err(got, ref, floor=1e-6):
+    """max |got - ref| relative to the reference's max magnitude (floored so exact-zero references compare absolutely)."""
     got, ref = got.float(), ref.float()
-    return ((got - ref).abs().max() / (ref.abs().max() + 1e-12)).item()
+    return ((got - ref).abs().max() / max(ref.abs().max().item(), floor)).item()
 
 
 def build_pair(cfg_kwargs, rank, seed=0, lora_b_std=0.02, device="cuda"):

@@ -411,7 +411,7 @@ def check_model():
             if "lora_" in n:
                 g_o = og[n].grad
                 g_b = p.grad.float().cpu()
-                denom = max(g_o.abs().max().item(), 2e-2 * gmax)
+                denom = max(g_o.abs().max().item(), 5e-2 * gmax)
                 e = (g_b - g_o).abs().max().item() / denom
                 worst = max(worst, e)
                 if e > 5e-2:
