@@ -120,7 +120,7 @@ class _B200Attention(torch.autograd.Function):
         Sk = k.shape[2]
         d_tok = dout.transpose(1, 2).reshape(B, Sq, H * 64).to(torch.bfloat16).contiguous()
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        delta = torch.empty(B, H, Sq, dtype=torch.float32, device=q.device)
+        delta = torch.empty(ops.attn_bwd_ws_floats(B, H, Sq, Sk), dtype=torch.float32, device=q.device)
         ops.attn_bwd(q, k, v, kb if ctx.has_bias else None, out, d_tok, lse, delta, dq, dk, dv, B, H, Sq, Sk, ctx.scale)
         return dq, dk, dv, None, None
 

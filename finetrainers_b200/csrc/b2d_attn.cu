@@ -156,6 +156,47 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
             tc_fence_after();
             const int kv0 = j * TILE;
             const bool fast = (kb == nullptr) && (kv0 + TILE <= p.Sk);  // full tile, no bias: no per-element masks
+            bool done = false;
+            if (fast && j > 0) {
+                // ---- optimistic single pass: exponentiate against the running max while tracking this tile's max; the
+                // running max is only replaced when a row grows by more than 2^8, which after the first tiles is rare.
+                mbar_wait(pv_done, (j - 1) & 1);  // P buffer free, O quiescent
+                tc_fence_after();
+                float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
+                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                const float nm = -m_run;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tS + lane_off + c * 32, v);
+                    tmem_ld_wait();
+                    float pv[32];
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) {
+                        const float a0 = __uint_as_float(v[e]), a1 = __uint_as_float(v[e + 1]);
+                        const float a2 = __uint_as_float(v[e + 2]), a3 = __uint_as_float(v[e + 3]);
+                        t0 = fmaxf(t0, a0); t1 = fmaxf(t1, a1); t2 = fmaxf(t2, a2); t3 = fmaxf(t3, a3);
+                        pv[e] = fast_exp2(fmaf(a0, p.scale_log2, nm));
+                        pv[e + 1] = fast_exp2(fmaf(a1, p.scale_log2, nm));
+                        pv[e + 2] = fast_exp2(fmaf(a2, p.scale_log2, nm));
+                        pv[e + 3] = fast_exp2(fmaf(a3, p.scale_log2, nm));
+                        l0 += pv[e]; l1 += pv[e + 1]; l2 += pv[e + 2]; l3 += pv[e + 3];
+                    }
+                    uint8_t* chunk = sP + (c >> 1) * TILE_BYTES;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 w = make_uint4(pack_bf16x2(pv[u * 8], pv[u * 8 + 1]), pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]),
+                                             pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]), pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]));
+                        *reinterpret_cast<uint4*>(chunk + sw128_off(r, (c & 1) * 4 + u)) = w;
+                    }
+                }
+                const float mxo = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) * p.scale_log2;
+                if (!__any_sync(0xffffffffu, (mxo - m_run) > 8.0f)) {
+                    l_run += (l0 + l1) + (l2 + l3);
+                    done = true;
+                }
+            }
+            if (!done) {
             // ---- pass 1: row max (log2 domain); 4 independent accumulators keep the FMNMX chain short
             float mx;
             if (fast) {
@@ -256,6 +297,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                 }
             }
             l_run += (l0 + l1) + (l2 + l3);
+            }  // !done
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(p_full);
@@ -298,7 +340,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
 // ================================================================================================
 // delta[b,h,q] = sum_d out[b,q,h,d] * dout[b,q,h,d]     (8 lanes per head-row)
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                                  float* __restrict__ delta, int B, int H, int Sq) {
+                                  const float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ nlse2,
+                                  int B, int H, int Sq) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * Sq * H * 8;
     const bool ok = t < total;
@@ -317,7 +360,9 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
         const long long bq = hr / H;
         const int q = (int)(bq % Sq);
         const int b = (int)(bq / Sq);
-        delta[((long long)b * H + h) * Sq + q] = acc;
+        const long long o = ((long long)b * H + h) * Sq + q;
+        delta[o] = acc;
+        nlse2[o] = -lse[o] * LOG2E;  // exponent offset in the log2 domain, consumed by the dK/dV pass
     }
 }
 
@@ -326,8 +371,12 @@ struct AttnBwdParams {
     const float* key_bias;               // [B, Sk] or null
     const float* lse;                    // [B, H, Sq]
     const float* delta;                  // [B, H, Sq]
+    const float* nlse2;                  // [B, H, Sq]  = -lse * log2(e)
     __nv_bfloat16* out1;                 // DKV: dV [B,H,Sk,64]
     __nv_bfloat16* out2;                 // DKV: dK [B,H,Sk,64];  !DKV: dQ [B,H,Sq,64]
+    float* acc1;                         // split mode (gridDim.z > 1): fp32 accumulators, atomically added, same layout
+    float* acc2;
+    int y_per_split;                     // streamed tiles per z-slice
     int B, H, Sq, Sk;
     float scale, scale_log2;
 };
@@ -339,7 +388,7 @@ template <int TY>
 struct BwdCfg {
     static constexpr int Y_BYTES = TY * HD * 2;           // one streamed tile  [TY x 64] bf16
     static constexpr int PS_BYTES = TILE * TY * 2;        // P^T or dS^T       [128 x TY] bf16 (TY/64 swizzled chunks)
-    static constexpr int SMEM = 2 * TILE_BYTES + BWD_Y_STAGES * 2 * Y_BYTES + 2 * PS_BYTES + 2 * 2 * TY * 4 + 1024 + 256;
+    static constexpr int SMEM = 2 * TILE_BYTES + BWD_Y_STAGES * 2 * Y_BYTES + 2 * PS_BYTES + BWD_Y_STAGES * 2 * TY * 4 + 1024 + 256;
     static constexpr int TMEM_COLS = (2 * TY + 128 <= 256) ? 256 : 512;
 };
 
@@ -353,9 +402,9 @@ __global__ void __launch_bounds__(ATT_THREADS, (TY == 64 ? 2 : 1)) attn_bwd_kern
     uint8_t* sY = sX2 + TILE_BYTES;                          // stage s: Y1 at +s*2*Y_BYTES, Y2 right after
     uint8_t* sP = sY + BWD_Y_STAGES * 2 * Cfg::Y_BYTES;      // P^T (DKV only)
     uint8_t* sDS = sP + Cfg::PS_BYTES;
-    float* sColA = reinterpret_cast<float*>(sDS + Cfg::PS_BYTES);  // [2][TY]
-    float* sColD = sColA + 2 * TY;                                  // [2][TY]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sColD + 2 * TY);
+    float* sColA = reinterpret_cast<float*>(sDS + Cfg::PS_BYTES);  // [stages][TY]  exponent offsets of the streamed tile
+    float* sColD = sColA + BWD_Y_STAGES * TY;                        // [stages][TY]  delta of the streamed tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sColD + BWD_Y_STAGES * TY);
     uint64_t* x_full = bars;
     uint64_t* y_full = bars + 1;   // [2]
     uint64_t* y_empty = bars + 3;  // [2]
@@ -370,7 +419,10 @@ __global__ void __launch_bounds__(ATT_THREADS, (TY == 64 ? 2 : 1)) attn_bwd_kern
     const int b = bh / p.H, h = bh % p.H;
     const int rowsX = DKV ? p.Sk : p.Sq;
     const int rowsY = DKV ? p.Sq : p.Sk;
-    const int n_y = (rowsY + TY - 1) / TY;
+    const int n_y_all = (rowsY + TY - 1) / TY;
+    const int y0 = blockIdx.z * p.y_per_split;                     // this CTA streams tiles [y0, y1)
+    const int y1 = min(n_y_all, y0 + p.y_per_split);
+    const int n_y = y1 - y0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmX1);
@@ -404,11 +456,19 @@ __global__ void __launch_bounds__(ATT_THREADS, (TY == 64 ? 2 : 1)) attn_bwd_kern
             tma_load_4d(sX2, &p.tmX2, x_full, 0, h, x0, b);
             int stage = 0;
             uint32_t phase = 0;
-            for (int i = 0; i < n_y; ++i) {
+            for (int it = 0; it < n_y; ++it) {
+                const int i = y0 + it;
                 mbar_wait(&y_empty[stage], phase ^ 1);
-                mbar_expect_tx(&y_full[stage], 2 * Cfg::Y_BYTES);
+                // DKV: the per-query exponent offsets (-lse*log2e) and delta of a full tile ride along with the tile
+                const bool colvec = DKV && ((i + 1) * TY <= rowsY) && ((rowsY & 3) == 0);
+                mbar_expect_tx(&y_full[stage], 2 * Cfg::Y_BYTES + (colvec ? 2 * TY * 4 : 0));
                 tma_load_4d(sY + stage * 2 * Cfg::Y_BYTES, &p.tmY1, &y_full[stage], 0, h, i * TY, b);
                 tma_load_4d(sY + stage * 2 * Cfg::Y_BYTES + Cfg::Y_BYTES, &p.tmY2, &y_full[stage], 0, h, i * TY, b);
+                if (colvec) {
+                    const long long off = ((long long)b * p.H + h) * p.Sq + (long long)i * TY;
+                    bulk_load_1d(sColA + stage * TY, p.nlse2 + off, TY * 4, &y_full[stage]);
+                    bulk_load_1d(sColD + stage * TY, p.delta + off, TY * 4, &y_full[stage]);
+                }
                 if (++stage == BWD_Y_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -420,7 +480,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (TY == 64 ? 2 : 1)) attn_bwd_kern
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t aX1 = smem_u32(sX1), aX2 = smem_u32(sX2), aP = smem_u32(sP), aDS = smem_u32(sDS);
-            for (int i = 0; i < n_y; ++i) {
+            for (int i = 0; i < n_y; ++i) {  // i = local iteration index
                 mbar_wait(&y_full[stage], phase);
                 tc_fence_after();
                 const uint32_t aY1 = smem_u32(sY + stage * 2 * Cfg::Y_BYTES), aY2 = aY1 + Cfg::Y_BYTES;
@@ -467,27 +527,39 @@ __global__ void __launch_bounds__(ATT_THREADS, (TY == 64 ? 2 : 1)) attn_bwd_kern
             rowD = row_ok ? p.delta[bhoff * p.Sq + xrow] : 0.f;
         }
         if (!row_ok) rowA = -INFINITY;
-        for (int i = 0; i < n_y; ++i) {
-            // column vectors of this streamed tile (double-buffered by parity)
-            float* cA = sColA + (i & 1) * TY;
-            float* cD = sColD + (i & 1) * TY;
-            if (tid128 < TY) {
-                const int ycol = i * TY + tid128;
-                const bool ok = ycol < rowsY;
-                if (DKV) {
-                    cA[tid128] = ok ? -p.lse[bhoff * p.Sq + ycol] * LOG2E : -INFINITY;
-                    cD[tid128] = ok ? p.delta[bhoff * p.Sq + ycol] : 0.f;
-                } else {
-                    cA[tid128] = ok ? (p.key_bias ? p.key_bias[(long long)b * p.Sk + ycol] * LOG2E : 0.f) : -INFINITY;
-                    cD[tid128] = 0.f;
+        int cstage = 0;
+        uint32_t cphase = 0;
+        for (int it = 0; it < n_y; ++it) {
+            const int i = y0 + it;
+            float* cA = sColA + cstage * TY;
+            float* cD = sColD + cstage * TY;
+            const bool full_tile = (i + 1) * TY <= rowsY;
+            // fast path: DKV -> column vectors arrive by bulk copy with the tile; dQ (self-attention) -> no column terms
+            const bool col_by_copy = DKV && full_tile && ((rowsY & 3) == 0);
+            const bool no_col = !DKV && full_tile && (p.key_bias == nullptr);
+            if (!col_by_copy && !no_col) {
+                // slow path (ragged tail / key bias): the 128 threads fill the column vectors themselves
+                if (tid128 < TY) {
+                    const int ycol = i * TY + tid128;
+                    const bool ok = ycol < rowsY;
+                    if (DKV) {
+                        cA[tid128] = ok ? -p.lse[bhoff * p.Sq + ycol] * LOG2E : -INFINITY;
+                        cD[tid128] = ok ? p.delta[bhoff * p.Sq + ycol] : 0.f;
+                    } else {
+                        cA[tid128] = ok ? (p.key_bias ? p.key_bias[(long long)b * p.Sk + ycol] * LOG2E : 0.f) : -INFINITY;
+                        cD[tid128] = 0.f;
+                    }
                 }
+                named_bar_sync(1, 128);
             }
-            named_bar_sync(1, 128);
-            mbar_wait(s_full, i & 1);
+            if (col_by_copy) {
+                mbar_wait(&y_full[cstage], cphase);  // acquire the bulk-copied vectors (the MMA warp waits on it too)
+            }
+            mbar_wait(s_full, it & 1);
             tc_fence_after();
             // P / dS smem buffers are free once the previous iteration's MMAs have completed
-            if (i > 0) {
-                mbar_wait(mm_done, (i - 1) & 1);
+            if (it > 0) {
+                mbar_wait(mm_done, (it - 1) & 1);
                 tc_fence_after();
             }
 #pragma unroll 1
@@ -497,14 +569,21 @@ __global__ void __launch_bounds__(ATT_THREADS, (TY == 64 ? 2 : 1)) attn_bwd_kern
                 tmem_ld32(tDP + lane_off + c * 32, dv);
                 tmem_ld_wait();
                 float pe[32], ds[32];
+                if (no_col) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int cc = c * 32 + e;
-                    float x = fmaf(__uint_as_float(sv[e]), p.scale_log2, rowA + cA[cc]);
-                    float pp = fast_exp2(x);
-                    float dd = __uint_as_float(dv[e]) - (DKV ? cD[cc] : rowD);
-                    pe[e] = pp;
-                    ds[e] = pp * dd * p.scale;
+                    for (int e = 0; e < 32; ++e) {
+                        float pp = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, rowA));
+                        pe[e] = pp;
+                        ds[e] = pp * (__uint_as_float(dv[e]) - rowD);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int cc = c * 32 + e;
+                        float pp = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, rowA + cA[cc]));
+                        pe[e] = pp;
+                        ds[e] = pp * (__uint_as_float(dv[e]) - (DKV ? cD[cc] : rowD));
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -522,27 +601,40 @@ __global__ void __launch_bounds__(ATT_THREADS, (TY == 64 ? 2 : 1)) attn_bwd_kern
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(ds_full);
+            if (++cstage == BWD_Y_STAGES) { cstage = 0; cphase ^= 1; }
         }
-        // ---- epilogue: accumulators -> [B,H,rowsX,64] bf16
-        mbar_wait(mm_done, (n_y - 1) & 1);
-        tc_fence_after();
+        // ---- epilogue: accumulators -> [B,H,rowsX,64] bf16 (or fp32 atomics when the streamed range is split over z)
+        if (n_y > 0) {
+            mbar_wait(mm_done, (n_y - 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-        for (int which = DKV ? 0 : 1; which < 2; ++which) {
-            __nv_bfloat16* dst = (which == 0 ? p.out1 : p.out2) + (bhoff * rowsX + xrow) * HD;
-            const uint32_t tacc = which == 0 ? tO1 : tO2;
+            for (int which = DKV ? 0 : 1; which < 2; ++which) {
+                const long long ro = (bhoff * rowsX + xrow) * HD;
+                const uint32_t tacc = which == 0 ? tO1 : tO2;
+                const float osc = which == 0 ? 1.f : p.scale;  // dS was kept unscaled: dK, dQ pick up the scale here
+                float* facc = which == 0 ? p.acc1 : p.acc2;
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                tmem_ld32(tacc + lane_off + c * 32, v);
-                tmem_ld_wait();
-                if (row_ok) {
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tacc + lane_off + c * 32, v);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint4 w = make_uint4(pack_bf16x2(__uint_as_float(v[u * 8]), __uint_as_float(v[u * 8 + 1])),
-                                             pack_bf16x2(__uint_as_float(v[u * 8 + 2]), __uint_as_float(v[u * 8 + 3])),
-                                             pack_bf16x2(__uint_as_float(v[u * 8 + 4]), __uint_as_float(v[u * 8 + 5])),
-                                             pack_bf16x2(__uint_as_float(v[u * 8 + 6]), __uint_as_float(v[u * 8 + 7])));
-                        *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = w;
+                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * osc);
+                    if (row_ok) {
+                        if (gridDim.z > 1) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) atomicAdd(facc + ro + c * 32 + e, __uint_as_float(v[e]));
+                        } else {
+                            __nv_bfloat16* dst = (which == 0 ? p.out1 : p.out2) + ro;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                uint4 w = make_uint4(pack_bf16x2(__uint_as_float(v[u * 8]), __uint_as_float(v[u * 8 + 1])),
+                                                     pack_bf16x2(__uint_as_float(v[u * 8 + 2]), __uint_as_float(v[u * 8 + 3])),
+                                                     pack_bf16x2(__uint_as_float(v[u * 8 + 4]), __uint_as_float(v[u * 8 + 5])),
+                                                     pack_bf16x2(__uint_as_float(v[u * 8 + 6]), __uint_as_float(v[u * 8 + 7])));
+                                *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = w;
+                            }
+                        }
                     }
                 }
             }
@@ -553,6 +645,14 @@ __global__ void __launch_bounds__(ATT_THREADS, (TY == 64 ? 2 : 1)) attn_bwd_kern
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem, Cfg::TMEM_COLS);
+    }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        float4 v = *reinterpret_cast<const float4*>(src + i);
+        *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     }
 }
 
@@ -619,8 +719,8 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     {
         long long total = (long long)B * Sq * H * 8;
-        attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)out,
-                                                                           (const __nv_bfloat16*)dout, delta_ws, B, H, Sq);
+        attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, lse, delta_ws, delta_ws + (long long)B * H * Sq, B, H, Sq);
         B2D_CHECK_LAUNCH("attn_delta");
     }
     constexpr int TY = 64;
@@ -636,18 +736,39 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
     if ((rc = make_head_map(&mdOy, dout, B, H, Sq, 64, (long long)H * 64, (long long)Sq * H * 64, TY))) return rc;
     AttnBwdParams p;
     memset(&p, 0, sizeof(p));
-    p.key_bias = key_bias; p.lse = lse; p.delta = delta_ws;
+    p.key_bias = key_bias; p.lse = lse; p.delta = delta_ws; p.nlse2 = delta_ws + (long long)B * H * Sq;
     p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
     p.scale = scale; p.scale_log2 = scale * LOG2E;
-    // dK, dV
+    // dK, dV.  With few key tiles (cross attention: Sk = 128 -> B*H CTAs) the query range is split over gridDim.z and
+    // the partial dK/dV are accumulated with fp32 atomics in the tail of delta_ws, then rounded to bf16.
     p.tmX1 = mK; p.tmX2 = mV; p.tmY1 = mQy; p.tmY2 = mdOy;
     p.out1 = (__nv_bfloat16*)dv; p.out2 = (__nv_bfloat16*)dk;
+    const int n_yq = (Sq + TY - 1) / TY;
+    const int kv_ctas = ((Sk + TILE - 1) / TILE) * B * H;
+    int splits = 1;
+    if (kv_ctas < 96 && Sk <= 512 && n_yq >= 8) splits = min(min(8, n_yq / 4), (2 * 148 + kv_ctas - 1) / kv_ctas);
     if ((rc = set_smem((const void*)attn_bwd_kernel<true, TY>, BwdCfg<TY>::SMEM, "attn_bwd_dkv"))) return rc;
-    attn_bwd_kernel<true, TY><<<dim3((Sk + TILE - 1) / TILE, B * H), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
-    B2D_CHECK_LAUNCH("attn_bwd_dkv");
+    p.y_per_split = (n_yq + splits - 1) / splits;
+    if (splits > 1) {
+        const long long n_kv = (long long)B * H * Sk * HD;
+        p.acc1 = delta_ws + 2LL * B * H * Sq;
+        p.acc2 = p.acc1 + n_kv;
+        cudaError_t e = cudaMemsetAsync(p.acc1, 0, 2 * n_kv * sizeof(float), st);
+        if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "attn_bwd memset: %s", cudaGetErrorString(e));
+        attn_bwd_kernel<true, TY><<<dim3((Sk + TILE - 1) / TILE, B * H, splits), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
+        B2D_CHECK_LAUNCH("attn_bwd_dkv(split)");
+        f32_to_bf16_kernel<<<(unsigned)((n_kv / 4 + 255) / 256), 256, 0, st>>>(p.acc1, (__nv_bfloat16*)dv, n_kv);
+        f32_to_bf16_kernel<<<(unsigned)((n_kv / 4 + 255) / 256), 256, 0, st>>>(p.acc2, (__nv_bfloat16*)dk, n_kv);
+        B2D_CHECK_LAUNCH("attn_bwd_dkv(convert)");
+    } else {
+        attn_bwd_kernel<true, TY><<<dim3((Sk + TILE - 1) / TILE, B * H), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
+        B2D_CHECK_LAUNCH("attn_bwd_dkv");
+    }
+    p.acc1 = p.acc2 = nullptr;
     // dQ
     p.tmX1 = mQ; p.tmX2 = mdO; p.tmY1 = mKy; p.tmY2 = mVy;
     p.out1 = nullptr; p.out2 = (__nv_bfloat16*)dq;
+    p.y_per_split = (Sk + TY - 1) / TY;
     if ((rc = set_smem((const void*)attn_bwd_kernel<false, TY>, BwdCfg<TY>::SMEM, "attn_bwd_dq"))) return rc;
     attn_bwd_kernel<false, TY><<<dim3((Sq + TILE - 1) / TILE, B * H), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
     B2D_CHECK_LAUNCH("attn_bwd_dq");

@@ -44,6 +44,7 @@ __device__ __forceinline__ float2 block_sum2(float a, float b) {
 // ------------------------------------------------------------------------------------------------
 // norm + modulate
 // ------------------------------------------------------------------------------------------------
+template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_fwd_kernel(
     const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ shift_tab,
     const __nv_bfloat16* __restrict__ shift_emb, const __nv_bfloat16* __restrict__ scale_tab,
@@ -52,10 +53,10 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_fwd_kernel(
     const int row = blockIdx.x;
     const int b = row / rows_per_sample;
     const __nv_bfloat16* xr = x + (long long)row * D;
-    float v[MAX_CHUNKS][8];
+    float v[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAX_CHUNKS; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
             unpack8(ldg16(xr + col), v[c]);
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_fwd_kernel(
         mean = tot.x / D;
         float var = 0.f;
 #pragma unroll
-        for (int c = 0; c < MAX_CHUNKS; ++c) {
+        for (int c = 0; c < NCH; ++c) {
             const int col = (c * ROW_THREADS + threadIdx.x) * 8;
             if (col < D) {
 #pragma unroll
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_fwd_kernel(
         rstd = rsqrtf(tot.y / D + eps);
     }
 #pragma unroll
-    for (int c = 0; c < MAX_CHUNKS; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
             float sh[8], sc[8], t[8];
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_fwd_kernel(
     }
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dx_in,
     __nv_bfloat16* __restrict__ dx_out, const __nv_bfloat16* __restrict__ scale_tab,
@@ -111,10 +113,10 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
     const int row = blockIdx.x;
     const int b = row / rows_per_sample;
     const long long ro = (long long)row * D;
-    float xv[MAX_CHUNKS][8], g[MAX_CHUNKS][8];
+    float xv[NCH][8], g[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAX_CHUNKS; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
             unpack8(ldg16(x + ro + col), xv[c]);
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
         mean = tot.x / D;
         float var = 0.f;
 #pragma unroll
-        for (int c = 0; c < MAX_CHUNKS; ++c) {
+        for (int c = 0; c < NCH; ++c) {
             const int col = (c * ROW_THREADS + threadIdx.x) * 8;
             if (col < D) {
 #pragma unroll
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
     // g = dy * (1 + scale);  xhat = (x - mean) * rstd;  a = sum(g), c = sum(g * xhat)
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAX_CHUNKS; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
             float sc[8], t[8], d[8];
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
     const float mg = layer_norm ? t2.x / D : 0.f;
     const float mgx = t2.y / D;
 #pragma unroll
-    for (int c = 0; c < MAX_CHUNKS; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
             float o[8];
@@ -209,6 +211,7 @@ __global__ void colscale_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
 // ------------------------------------------------------------------------------------------------
 // q/k RMSNorm (affine, across all heads) + RoPE + head split:  src[row, col_off + c] -> dst[b, h, s, d]
 // ------------------------------------------------------------------------------------------------
+template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS) qknorm_rope_fwd_kernel(
     const __nv_bfloat16* __restrict__ src, long long ld, long long col_off, const __nv_bfloat16* __restrict__ weight,
     const float* __restrict__ cosT, const float* __restrict__ sinT, __nv_bfloat16* __restrict__ dst, int S, int H,
@@ -217,10 +220,10 @@ __global__ void __launch_bounds__(ROW_THREADS) qknorm_rope_fwd_kernel(
     const int row = blockIdx.x;
     const int b = row / S, s = row % S;
     const __nv_bfloat16* xr = src + (long long)row * ld + col_off;
-    float v[MAX_CHUNKS][8];
+    float v[NCH][8];
     float s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAX_CHUNKS; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
             unpack8(ldg16(xr + col), v[c]);
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(ROW_THREADS) qknorm_rope_fwd_kernel(
     float rstd = 1.f;
     if (norm) rstd = rsqrtf(block_sum2(s2, 0.f).x / D + eps);
 #pragma unroll
-    for (int c = 0; c < MAX_CHUNKS; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
             float n[8];
@@ -246,15 +249,15 @@ __global__ void __launch_bounds__(ROW_THREADS) qknorm_rope_fwd_kernel(
             }
             float o[8];
             if (cosT != nullptr) {
-                const float4* cp = reinterpret_cast<const float4*>(cosT + (long long)s * D + col);
-                const float4* sp = reinterpret_cast<const float4*>(sinT + (long long)s * D + col);
-                float4 c0 = cp[0], c1 = cp[1], s0 = sp[0], s1 = sp[1];
-                const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                // tables hold one (cos, sin) per rotary PAIR: [S, D/2] fp32 (the reference's repeat_interleave(2) is implicit)
+                const float4 c4 = *reinterpret_cast<const float4*>(cosT + ((long long)s * D + col) / 2);
+                const float4 s4 = *reinterpret_cast<const float4*>(sinT + ((long long)s * D + col) / 2);
+                const float cs[4] = {c4.x, c4.y, c4.z, c4.w};
+                const float sn[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
-                    o[e] = n[e] * cs[e] - n[e + 1] * sn[e];
-                    o[e + 1] = n[e + 1] * cs[e + 1] + n[e] * sn[e + 1];
+                    o[e] = n[e] * cs[e >> 1] - n[e + 1] * sn[e >> 1];
+                    o[e + 1] = n[e + 1] * cs[e >> 1] + n[e] * sn[e >> 1];
                 }
             } else {
 #pragma unroll
@@ -266,6 +269,7 @@ __global__ void __launch_bounds__(ROW_THREADS) qknorm_rope_fwd_kernel(
     }
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS) qknorm_rope_bwd_kernel(
     const __nv_bfloat16* __restrict__ dyh, const __nv_bfloat16* __restrict__ x, long long ld, long long col_off,
     const __nv_bfloat16* __restrict__ weight, const float* __restrict__ cosT, const float* __restrict__ sinT,
@@ -273,12 +277,12 @@ __global__ void __launch_bounds__(ROW_THREADS) qknorm_rope_bwd_kernel(
     const int D = H * 64;
     const int row = blockIdx.x;
     const int b = row / S, s = row % S;
-    float xv[MAX_CHUNKS][8], g[MAX_CHUNKS][8];
+    float xv[NCH][8], g[NCH][8];
     float s2 = 0.f;
     if (norm) {
         const __nv_bfloat16* xr = x + (long long)row * ld + col_off;
 #pragma unroll
-        for (int c = 0; c < MAX_CHUNKS; ++c) {
+        for (int c = 0; c < NCH; ++c) {
             const int col = (c * ROW_THREADS + threadIdx.x) * 8;
             if (col < D) {
                 unpack8(ldg16(xr + col), xv[c]);
@@ -291,22 +295,21 @@ __global__ void __launch_bounds__(ROW_THREADS) qknorm_rope_bwd_kernel(
     if (norm) rstd = rsqrtf(block_sum2(s2, 0.f).x / D + eps);
     float sgx = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAX_CHUNKS; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
             const int h = col >> 6, d = col & 63;
             float dy[8], dn[8];
             unpack8(ldg16(dyh + (((long long)b * H + h) * S + s) * 64 + d), dy);
             if (cosT != nullptr) {
-                const float4* cp = reinterpret_cast<const float4*>(cosT + (long long)s * D + col);
-                const float4* sp = reinterpret_cast<const float4*>(sinT + (long long)s * D + col);
-                float4 c0 = cp[0], c1 = cp[1], s0 = sp[0], s1 = sp[1];
-                const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float4 c4 = *reinterpret_cast<const float4*>(cosT + ((long long)s * D + col) / 2);
+                const float4 s4 = *reinterpret_cast<const float4*>(sinT + ((long long)s * D + col) / 2);
+                const float cs[4] = {c4.x, c4.y, c4.z, c4.w};
+                const float sn[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
-                    dn[e] = dy[e] * cs[e] + dy[e + 1] * sn[e + 1];
-                    dn[e + 1] = dy[e + 1] * cs[e + 1] - dy[e] * sn[e];
+                    dn[e] = dy[e] * cs[e >> 1] + dy[e + 1] * sn[e >> 1];
+                    dn[e + 1] = dy[e + 1] * cs[e >> 1] - dy[e] * sn[e >> 1];
                 }
             } else {
 #pragma unroll
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(ROW_THREADS) qknorm_rope_bwd_kernel(
     float mgx = 0.f;
     if (norm) mgx = block_sum2(sgx, 0.f).x / D;
 #pragma unroll
-    for (int c = 0; c < MAX_CHUNKS; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
             float o[8];
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(ROW_THREADS) qknorm_rope_bwd_kernel(
     }
 }
 
-// RoPE table: diffusers LTXVideoRotaryPosEmbed, fp32.  One thread per (s, pair).
+// RoPE table: diffusers LTXVideoRotaryPosEmbed, fp32, one (cos, sin) per rotary pair: [S, D/2].  One thread per (s, pair).
 __global__ void rope_table_kernel(float* __restrict__ cosT, float* __restrict__ sinT, int F, int H, int W, int D,
                                   float sf, float sh, float sw) {
     const int nf = D / 6;
@@ -368,10 +371,8 @@ __global__ void rope_table_kernel(float* __restrict__ cosT, float* __restrict__ 
         c = cosf(ang);
         sn = sinf(ang);
     }
-    cosT[(long long)s * D + col] = c;
-    cosT[(long long)s * D + col + 1] = c;
-    sinT[(long long)s * D + col] = sn;
-    sinT[(long long)s * D + col + 1] = sn;
+    cosT[(long long)s * pairs + pr] = c;
+    sinT[(long long)s * pairs + pr] = sn;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -505,6 +506,15 @@ __global__ void adamw_clip_kernel(float* __restrict__ p, float* __restrict__ g, 
 using namespace b2d;
 #define STREAM reinterpret_cast<cudaStream_t>(stream)
 
+// instantiate the row kernels for 1..4 chunks of 2048 columns (registers scale with the chunk count)
+#define ROW_DISPATCH(D_, KERNEL, GRID, ...)                                             \
+    do {                                                                                \
+        const int nch__ = ((D_) + 8 * ROW_THREADS - 1) / (8 * ROW_THREADS);             \
+        if (nch__ <= 1) KERNEL<1><<<GRID, ROW_THREADS, 0, STREAM>>>(__VA_ARGS__);       \
+        else if (nch__ == 2) KERNEL<2><<<GRID, ROW_THREADS, 0, STREAM>>>(__VA_ARGS__);  \
+        else KERNEL<4><<<GRID, ROW_THREADS, 0, STREAM>>>(__VA_ARGS__);                  \
+    } while (0)
+
 static int check_rowop(int rows, int D, int rps) {
     if (rows <= 0 || D <= 0 || rps <= 0) return set_error(B2D_ERR_SHAPE, "rows/D/rows_per_sample must be positive");
     if (D % 8 != 0 || D > 8 * ROW_THREADS * MAX_CHUNKS) return set_error(B2D_ERR_SHAPE, "D=%d must be a multiple of 8 and <= %d", D, 8 * ROW_THREADS * MAX_CHUNKS);
@@ -516,7 +526,7 @@ extern "C" int b2d_norm_modulate_fwd(const void* x, void* y, const void* shift_t
                                      int32_t D, int32_t rows_per_sample, float eps, int32_t layer_norm, void* stream) {
     B2D_BIND(x);
     if (int rc = check_rowop(rows, D, rows_per_sample)) return rc;
-    norm_modulate_fwd_kernel<<<rows, ROW_THREADS, 0, STREAM>>>(
+    ROW_DISPATCH(D, norm_modulate_fwd_kernel, rows,
         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)shift_tab, (const __nv_bfloat16*)shift_emb,
         (const __nv_bfloat16*)scale_tab, (const __nv_bfloat16*)scale_emb, emb_stride, D, rows_per_sample, eps, layer_norm);
     B2D_CHECK_LAUNCH("norm_modulate_fwd");
@@ -529,7 +539,7 @@ extern "C" int b2d_norm_modulate_bwd(const void* dy, const void* x, const void* 
                                      int32_t rows_per_sample, float eps, int32_t layer_norm, void* stream) {
     B2D_BIND(dy);
     if (int rc = check_rowop(rows, D, rows_per_sample)) return rc;
-    norm_modulate_bwd_kernel<<<rows, ROW_THREADS, 0, STREAM>>>(
+    ROW_DISPATCH(D, norm_modulate_bwd_kernel, rows,
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dx_in, (__nv_bfloat16*)dx_out,
         (const __nv_bfloat16*)scale_tab, (const __nv_bfloat16*)scale_emb, (const __nv_bfloat16*)gate2_tab,
         (const __nv_bfloat16*)gate2_emb, (__nv_bfloat16*)out2, emb_stride, D, rows_per_sample, eps, layer_norm);
@@ -556,7 +566,7 @@ extern "C" int b2d_qknorm_rope_fwd(const void* src, int64_t ld, int64_t col_off,
     B2D_BIND(src);
     if (int rc = check_rowop(B * S, H * 64, S)) return rc;
     if ((ld % 8) || (col_off % 8)) return set_error(B2D_ERR_ALIGN, "qknorm_rope: ld/col_off must be multiples of 8");
-    qknorm_rope_fwd_kernel<<<B * S, ROW_THREADS, 0, STREAM>>>((const __nv_bfloat16*)src, ld, col_off,
+    ROW_DISPATCH(H * 64, qknorm_rope_fwd_kernel, B * S, (const __nv_bfloat16*)src, ld, col_off,
                                                               (const __nv_bfloat16*)weight, (const float*)cos,
                                                               (const float*)sin, (__nv_bfloat16*)dst, S, H, norm, eps);
     B2D_CHECK_LAUNCH("qknorm_rope_fwd");
@@ -571,7 +581,7 @@ extern "C" int b2d_qknorm_rope_bwd(const void* dsrc_heads, const void* x, int64_
     if (int rc = check_rowop(B * S, H * 64, S)) return rc;
     if ((ld % 8) || (col_off % 8) || (ld_dx % 8) || (dx_col_off % 8))
         return set_error(B2D_ERR_ALIGN, "qknorm_rope_bwd: ld/col_off must be multiples of 8");
-    qknorm_rope_bwd_kernel<<<B * S, ROW_THREADS, 0, STREAM>>>(
+    ROW_DISPATCH(H * 64, qknorm_rope_bwd_kernel, B * S,
         (const __nv_bfloat16*)dsrc_heads, (const __nv_bfloat16*)x, ld, col_off, (const __nv_bfloat16*)weight,
         (const float*)cos, (const float*)sin, (__nv_bfloat16*)dx, ld_dx, dx_col_off, S, H, norm, eps);
     B2D_CHECK_LAUNCH("qknorm_rope_bwd");

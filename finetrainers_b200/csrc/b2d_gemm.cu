@@ -3,7 +3,8 @@
 //   warp 0      : TMA producer (one elected lane)     global -> 128B-swizzled smem ring (mbarrier full/empty)
 //   warp 1      : MMA issuer (one elected lane) + TMEM owner; tcgen05.mma 128 x BLOCK_N x 16, fp32 accumulators in TMEM,
 //                 double-buffered so the epilogue of tile i overlaps the main loop of tile i+1
-//   warps 2..5  : epilogue; tcgen05.ld (one accumulator row per thread) -> fused epilogue -> global
+//   warps 2..9  : epilogue (two warps per TMEM lane quarter, splitting the columns); tcgen05.ld (one accumulator row
+//                 per thread) -> fused epilogue -> global, side-operand loads prefetched one chunk ahead
 //
 // Operands may be K-major or MN-major (transposed views of row-major activations/weights), which covers
 // forward (x W^T), backward-dX (dY W) and backward-dW (dY^T X) without materialising transposes.
@@ -15,7 +16,7 @@ namespace b2d {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 
 struct GemmKParams {
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 128);
+            mbar_init(&tempty_bar[i], 256);
         }
         fence_mbar_init();
     }
@@ -218,7 +219,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         }
     } else {
         // ============================== epilogue warps ==============================
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        // 8 warps: warp w may only touch TMEM lanes [32*(w%4), +32); the two warps that share a lane quarter split the
+        // tile's columns.  Loads of residual / aux operands are issued one 32-column chunk ahead of their use.
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int NCH = BN / 32;
+        const int c_begin = half ? (NCH + 1) / 2 : 0;
+        const int c_end = half ? NCH : (NCH + 1) / 2;
+        const int epi = p.epi;
+        const __nv_bfloat16* side = (epi == B2D_EPI_GATE_RES) ? p.res : ((epi == B2D_EPI_MUL_DGELU) ? p.aux : nullptr);
+        const long long ldside = (epi == B2D_EPI_GATE_RES) ? p.ldres : p.ldaux;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
@@ -230,13 +240,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             const int row = mt * BLOCK_M + q * 32 + lane;
             const int n0 = nt * BN;
             const bool row_ok = row < p.M;
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
             const int b = (p.rows_per_sample > 0) ? (row_ok ? row / p.rows_per_sample : 0) : 0;
             const long long cbase = (long long)z * p.c_boff;
+            const __nv_bfloat16* side_row = side ? side + (long long)row * ldside : nullptr;
+            uint4 pf[4];
+            auto prefetch = [&](int c) {
+                if (side_row != nullptr && row_ok) {
+                    const int col0 = n0 + c * 32;
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8)
+                        if (col0 + j8 * 8 < p.N) pf[j8] = ld_global_16B(side_row + col0 + j8 * 8);
+                }
+            };
+            prefetch(c_begin);
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
+                uint4 cur[4] = {pf[0], pf[1], pf[2], pf[3]};
+                if (c + 1 < c_end) prefetch(c + 1);
                 uint32_t r[32];
                 tmem_ld32(taddr + c * 32, r);
                 tmem_ld_wait();
@@ -245,7 +268,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-                    const int epi = p.epi;
                     if (epi == B2D_EPI_F32_ATOMIC) {
                         float* o = reinterpret_cast<float*>(p.out) + cbase + (long long)row * p.ldc + col0;
 #pragma unroll
@@ -288,12 +310,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                                     v[j] = (epi == B2D_EPI_GELU) ? gelu_tanh(v[j]) : silu(v[j]);
                                 }
                             } else if (epi == B2D_EPI_GATE_RES) {
-                                const __nv_bfloat16* rp = p.res + (long long)row * p.ldres + col0;
 #pragma unroll
                                 for (int j8 = 0; j8 < 4; ++j8) {
                                     if (col0 + j8 * 8 < p.N) {
-                                        uint4 rr = ld_global_16B(rp + j8 * 8);
-                                        const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+                                        const uint32_t rw[4] = {cur[j8].x, cur[j8].y, cur[j8].z, cur[j8].w};
                                         float g[8];
                                         if (p.gate_table != nullptr) {
                                             uint4 gt = ld_global_16B(p.gate_table + col0 + j8 * 8);
@@ -332,12 +352,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                                 }
                                 has2 = (p.gate2_table != nullptr && p.out2 != nullptr);
                             } else if (epi == B2D_EPI_MUL_DGELU) {
-                                const __nv_bfloat16* ap = p.aux + (long long)row * p.ldaux + col0;
 #pragma unroll
                                 for (int j8 = 0; j8 < 4; ++j8) {
                                     if (col0 + j8 * 8 < p.N) {
-                                        uint4 aa = ld_global_16B(ap + j8 * 8);
-                                        const uint32_t aw[4] = {aa.x, aa.y, aa.z, aa.w};
+                                        const uint32_t aw[4] = {cur[j8].x, cur[j8].y, cur[j8].z, cur[j8].w};
 #pragma unroll
                                         for (int e = 0; e < 4; ++e) {
                                             v[j8 * 8 + 2 * e] *= dgelu_tanh(bf16_lo(aw[e]));

@@ -88,6 +88,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         "r"(c3)
         : "memory");
 }
+// 1-D bulk copy global -> shared (bytes % 16 == 0, 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 // smem (fp32 tile) --add--> global, through the TMA unit (used for dQ accumulation)
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
     asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
@@ -231,21 +238,27 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// GELU(tanh) and derivative, fp32
+// GELU(tanh) and derivative, fp32, on the MUFU tanh unit (tanh.approx.f32: rel. error 2^-11, below bf16 resolution)
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float gelu_tanh(float x) {
-    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-    float u = k0 * (x + k1 * x * x * x);
-    float t = 1.f - 2.f / (1.f + __expf(2.f * u));  // tanh(u)
-    return 0.5f * x * (1.f + t);
+    const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+    float x2 = x * x;
+    float t = tanh_approx(x * fmaf(k0k1, x2, k0));
+    float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
 }
 __device__ __forceinline__ float dgelu_tanh(float x) {
-    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
     float x2 = x * x;
-    float u = k0 * (x + k1 * x * x2);
-    float t = 1.f - 2.f / (1.f + __expf(2.f * u));
-    float du = k0 * (1.f + 3.f * k1 * x2);
-    return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * du;
+    float t = tanh_approx(x * fmaf(k0k1, x2, k0));
+    float du = fmaf(3.f * k0k1, x2, k0);
+    float s = fmaf(-t, t, 1.f);
+    return fmaf(0.5f * x * s, du, fmaf(0.5f, t, 0.5f));
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 }  // namespace b2d

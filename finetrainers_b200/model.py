@@ -354,7 +354,7 @@ class B200LTXTransformer(nn.Module):
         z("dqh", B, H, S, 64); z("dkh", B, H, S, 64); z("dvh", B, H, S, 64)
         z("dk2h", B, H, L, 64); z("dv2h", B, H, L, 64)
         z("dqkv", R, 3 * d); z("dq2", R, d); z("dkv2", RL, 2 * d)
-        z("delta", B, H, S, kw=f32)
+        z("delta", max(ops.attn_bwd_ws_floats(B, H, S, S), ops.attn_bwd_ws_floats(B, H, S, L)), kw=f32)
         self._ws[key] = ws
         return ws
 
@@ -364,7 +364,7 @@ class B200LTXTransformer(nn.Module):
         if t is None:
             d = self.cfg.inner_dim
             dev = self.proj_in.weight.device
-            cos = torch.empty(Fr * Hh * Ww, d, dtype=torch.float32, device=dev)
+            cos = torch.empty(Fr * Hh * Ww, d // 2, dtype=torch.float32, device=dev)
             sin = torch.empty_like(cos)
             # diffusers LTXVideoRotaryPosEmbed: grid * scale * patch / base (base_num_frames 20, base_h = base_w = 2048)
             ops.rope_table(cos, sin, Fr, Hh, Ww, d, rope_scale[0] * self.cfg.patch_size_t / 20.0,

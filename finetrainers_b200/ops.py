@@ -163,12 +163,19 @@ def attn_fwd(q, k, v, key_bias, out, lse, B, H, Sq, Sk, scale):
     return out
 
 
+def attn_bwd_ws_floats(B, H, Sq, Sk):
+    """fp32 elements b2d_attn_bwd needs in delta_ws (include/b2d.h)."""
+    return 2 * B * H * Sq + (2 * B * H * Sk * 64 if Sk <= 512 else 0)
+
+
 def attn_bwd(q, k, v, key_bias, out, dout, lse, delta_ws, dq, dk, dv, B, H, Sq, Sk, scale):
+    if delta_ws.numel() < attn_bwd_ws_floats(B, H, Sq, Sk):
+        raise _l.B2DError(f"attn_bwd workspace too small: {delta_ws.numel()} < {attn_bwd_ws_floats(B, H, Sq, Sk)} floats")
     with _Timed("attn_bwd"):
         check(_l.load().b2d_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(key_bias), _ptr(out), _ptr(dout), _ptr(lse),
                                      _ptr(delta_ws), _ptr(dq), _ptr(dk), _ptr(dv), B, H, Sq, Sk, C.c_float(scale),
                                      _stream()), "attn_bwd")
-    _count(3)
+    _count(3 if Sk > 512 else 6)
 
 
 def prep_noise_pack(latents, noise, mean, std, sigma, sigma_ff, x_t, target, B, Cc, F, HW):

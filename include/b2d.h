@@ -109,7 +109,7 @@ int b2d_colscale(const void* x, void* out, const void* tab, const void* emb, int
 /* ---------------------------------------------------------------------------------------------------------------
  * q/k RMSNorm-across-heads (affine) + 3-D RoPE + head split.
  *   src [rows, ld] bf16 (q, k, v at column offsets) -> q',k',v' in [B, H, S, 64].
- * rope cos/sin: fp32 [S, D] (NULL = no RoPE: cross attention).
+ * rope cos/sin: fp32 [S, D/2], one value per rotary pair (NULL = no RoPE: cross attention).
  * Replaces: diffusers LTXVideoAttentionProcessor2_0 (norm_q/norm_k, apply_rotary_emb patch.py:23-33, unflatten+transpose).
  * ------------------------------------------------------------------------------------------------------------- */
 int b2d_qknorm_rope_fwd(const void* src, int64_t ld, int64_t col_off, const void* weight, const void* cos,
@@ -119,7 +119,8 @@ int b2d_qknorm_rope_bwd(const void* dsrc_heads, const void* x, int64_t ld, int64
                         const void* cos, const void* sin, void* dx, int64_t ld_dx, int64_t dx_col_off, int32_t B,
                         int32_t S, int32_t H, int32_t norm, float eps, void* stream);
 
-/* RoPE table (diffusers LTXVideoRotaryPosEmbed.forward, called at patch.py:52): fp32 cos,sin [F*H*W, D]. */
+/* RoPE table (diffusers LTXVideoRotaryPosEmbed.forward, called at patch.py:52): fp32 cos,sin [F*H*W, D/2]
+ * (the reference's repeat_interleave(2) duplicates are not stored). */
 int b2d_rope_table(float* cos, float* sin, int32_t F, int32_t H, int32_t W, int32_t D, float sf, float sh, float sw,
                    void* stream);
 
@@ -131,7 +132,8 @@ int b2d_rope_table(float* cos, float* sin, int32_t F, int32_t H, int32_t W, int3
  * ------------------------------------------------------------------------------------------------------------- */
 int b2d_attn_fwd(const void* q, const void* k, const void* v, const float* key_bias, void* out, float* lse, int32_t B,
                  int32_t H, int32_t Sq, int32_t Sk, float scale, void* stream);
-/* dout [B,Sq,H*64] bf16; out as produced by fwd; dq,dk,dv [B,H,S,64] bf16; workspace: fp32 delta [B,H,Sq]. */
+/* dout [B,Sq,H*64] bf16; out as produced by fwd; dq,dk,dv [B,H,S,64] bf16; workspace delta_ws:
+ * 2*B*H*Sq floats, plus 2*B*H*Sk*64 floats when Sk <= 512 (fp32 dK/dV accumulators of the split cross-attention path). */
 int b2d_attn_bwd(const void* q, const void* k, const void* v, const float* key_bias, const void* out, const void* dout,
                  const float* lse, float* delta_ws, void* dq, void* dk, void* dv, int32_t B, int32_t H, int32_t Sq,
                  int32_t Sk, float scale, void* stream);

@@ -57,7 +57,7 @@ def test_attention_fwd_bwd_shapes(B, H, Sq, Sk, bias):
     dout = rnd(B, Sq, H * 64)
     ref.backward(dout.float().unflatten(2, (H, 64)).transpose(1, 2))
     dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
-    ws = torch.zeros(B, H, Sq, device="cuda")
+    ws = torch.zeros(ops.attn_bwd_ws_floats(B, H, Sq, Sk), device="cuda")
     ops.attn_bwd(q, k, v, kb, out, dout, lse, ws, dq, dk, dv, B, H, Sq, Sk, 0.125)
     assert rel_err(dq, qf.grad, 1e-2) < 2e-2 and rel_err(dk, kf.grad, 1e-2) < 2e-2 and rel_err(dv, vf.grad, 1e-2) < 2e-2
 

@@ -144,11 +144,12 @@ def test_rope_table_vs_oracle(ops):
     from oracle.ltx_oracle import ltx_rope_table
     Fr, Hh, Ww, D = 7, 16, 24, 2048
     S = Fr * Hh * Ww
-    cos, sin = torch.empty(S, D, device="cuda"), torch.empty(S, D, device="cuda")
+    cos, sin = torch.empty(S, D // 2, device="cuda"), torch.empty(S, D // 2, device="cuda")
     ops.rope_table(cos, sin, Fr, Hh, Ww, D, (8 / 25) / 20, 32 / 2048, 32 / 2048)
     rc, rs = ltx_rope_table(Fr, Hh, Ww, D, [8 / 25, 32, 32], 1, "cpu")
+    assert torch.equal(rc[0][:, 0::2], rc[0][:, 1::2])  # the reference table is pairwise constant
     # fp32 angles reach 1.6e4 rad: one ulp of the frequency is ~1e-3 rad, hence the 5e-3 absolute tolerance
-    assert (cos.cpu() - rc[0]).abs().max() < 5e-3 and (sin.cpu() - rs[0]).abs().max() < 5e-3
+    assert (cos.cpu() - rc[0][:, 0::2]).abs().max() < 5e-3 and (sin.cpu() - rs[0][:, 0::2]).abs().max() < 5e-3
 
 
 @pytest.mark.parametrize("which,norm,rope", [(0, True, True), (1, True, False), (2, False, False)])
@@ -158,10 +159,11 @@ def test_qknorm_rope_fwd_bwd(ops, which, norm, rope):
     D = H * 64
     ang = torch.randn(S, D // 2, device="cuda")
     cos, sin = ang.cos().repeat_interleave(2, -1).contiguous(), ang.sin().repeat_interleave(2, -1).contiguous()
+    cos_p, sin_p = ang.cos().contiguous(), ang.sin().contiguous()  # kernel tables: one value per rotary pair
     qkv = rnd(Bq * S, 3 * D)
     w = (1 + 0.1 * torch.randn(D, device="cuda")).bfloat16()
     dst = torch.empty(Bq, H, S, 64, device="cuda", dtype=torch.bfloat16)
-    ops.qknorm_rope_fwd(qkv, 3 * D, which * D, w, cos if rope else None, sin if rope else None, dst, Bq, S, H, norm, 1e-5)
+    ops.qknorm_rope_fwd(qkv, 3 * D, which * D, w, cos_p if rope else None, sin_p if rope else None, dst, Bq, S, H, norm, 1e-5)
     xf = qkv[:, which * D:(which + 1) * D].float().reshape(Bq, S, D).requires_grad_(True)
     n = F.rms_norm(xf, (D,), weight=w.float(), eps=1e-5) if norm else xf
     if rope:
@@ -172,7 +174,7 @@ def test_qknorm_rope_fwd_bwd(ops, which, norm, rope):
     dyh = rnd(Bq, H, S, 64)
     ref.backward(dyh.float())
     dx = torch.zeros(Bq * S, 3 * D, device="cuda", dtype=torch.bfloat16)
-    ops.qknorm_rope_bwd(dyh, qkv, 3 * D, which * D, w, cos if rope else None, sin if rope else None, dx, 3 * D, which * D,
+    ops.qknorm_rope_bwd(dyh, qkv, 3 * D, which * D, w, cos_p if rope else None, sin_p if rope else None, dx, 3 * D, which * D,
                         Bq, S, H, norm, 1e-5)
     assert rel_err(dx[:, which * D:(which + 1) * D], xf.grad.reshape(Bq * S, D)) < 1e-2
 
@@ -210,7 +212,7 @@ def test_golden_reference_vectors_on_gpu(ops, golden):
     m.weight.data = w.clone()
     ref = apply_rotary_emb(m(xq.view(2, S, 64)), (cos[None], sin[None]))  # oracle == reference (pinned in CPU tests)
     dst = torch.empty(2, H, S, 64, device="cuda", dtype=torch.bfloat16)
-    ops.qknorm_rope_fwd(xq.cuda(), 64, 0, w.cuda(), cos.cuda().contiguous(), sin.cuda().contiguous(), dst, 2, S, H, True, 1e-5)
+    ops.qknorm_rope_fwd(xq.cuda(), 64, 0, w.cuda(), ang.cos().cuda().contiguous(), ang.sin().cuda().contiguous(), dst, 2, S, H, True, 1e-5)
     assert (dst[:, 0].cpu().float() - ref.float()).abs().max() < 3e-2
 
 

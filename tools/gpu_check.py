@@ -199,21 +199,22 @@ def check_elem():
     # rope table vs oracle-style torch computation
     Fr, Hh, Ww = 7, 16, 24
     S = Fr * Hh * Ww
-    cos = torch.empty(S, D, device=dev); sin = torch.empty(S, D, device=dev)
+    cos = torch.empty(S, D // 2, device=dev); sin = torch.empty(S, D // 2, device=dev)
     sf, sh, sw = (8 / 25) / 20, 32 / 2048, 32 / 2048
     ops.rope_table(cos, sin, Fr, Hh, Ww, D, sf, sh, sw)
     from oracle.ltx_oracle import ltx_rope_table, apply_rotary_emb  # test-only
     rc, rs = ltx_rope_table(Fr, Hh, Ww, D, [8 / 25, 32, 32], 1, "cpu")
-    report("rope_table cos", cos.cpu(), rc[0], 5e-3)
-    report("rope_table sin", sin.cpu(), rs[0], 5e-3)
+    report("rope_table cos", cos.cpu(), rc[0][:, 0::2], 5e-3)
+    report("rope_table sin", sin.cpu(), rs[0][:, 0::2], 5e-3)
     cos = rc[0].to(dev).contiguous(); sin = rs[0].to(dev).contiguous()
+    cos_p = rc[0][:, 0::2].to(dev).contiguous(); sin_p = rs[0][:, 0::2].to(dev).contiguous()
 
     # qknorm + rope
     Bq, H = 2, 32
     qkv = rnd(Bq * S, 3 * D); w = (1 + 0.1 * torch.randn(D, device=dev)).bfloat16()
     dst = torch.empty(Bq, H, S, 64, device=dev, dtype=torch.bfloat16)
     for which, norm, rope in ((0, True, True), (1, True, False), (2, False, False)):
-        ops.qknorm_rope_fwd(qkv, 3 * D, which * D, w, cos if rope else None, sin if rope else None, dst, Bq, S, H, norm, 1e-5)
+        ops.qknorm_rope_fwd(qkv, 3 * D, which * D, w, cos_p if rope else None, sin_p if rope else None, dst, Bq, S, H, norm, 1e-5)
         xf = qkv[:, which * D:(which + 1) * D].float().reshape(Bq, S, D).requires_grad_(True)
         n = F.rms_norm(xf, (D,), weight=w.float(), eps=1e-5) if norm else xf
         if rope:
@@ -225,7 +226,7 @@ def check_elem():
         dyh = rnd(Bq, H, S, 64)
         ref.backward(dyh.float())
         dx = torch.zeros(Bq * S, 3 * D, device=dev, dtype=torch.bfloat16)
-        ops.qknorm_rope_bwd(dyh, qkv, 3 * D, which * D, w, cos if rope else None, sin if rope else None, dx, 3 * D,
+        ops.qknorm_rope_bwd(dyh, qkv, 3 * D, which * D, w, cos_p if rope else None, sin_p if rope else None, dx, 3 * D,
                             which * D, Bq, S, H, norm, 1e-5)
         report(f"qknorm_rope_bwd which={which}", dx[:, which * D:(which + 1) * D], xf.grad.reshape(Bq * S, D), 1e-2)
 
@@ -316,7 +317,7 @@ def check_attn():
         dout = rnd(B_, Sq, H * 64)
         ref.backward(dout.float().unflatten(2, (H, 64)).transpose(1, 2))
         dq = torch.zeros_like(q); dk = torch.zeros_like(k); dv = torch.zeros_like(v)
-        ws = torch.zeros(B_, H, Sq, device=dev)
+        ws = torch.zeros(ops.attn_bwd_ws_floats(B_, H, Sq, Sk), device=dev)
         try:
             ops.attn_bwd(q, k, v, bias, out, dout, lse, ws, dq, dk, dv, B_, H, Sq, Sk, scale)
             torch.cuda.synchronize()
@@ -330,7 +331,7 @@ def check_attn():
     q = rnd(B_, H, S, 64); k = rnd(B_, H, S, 64); v = rnd(B_, H, S, 64)
     out = torch.zeros(B_, S, H * 64, device=dev, dtype=torch.bfloat16); lse = torch.zeros(B_, H, S, device=dev)
     dout = rnd(B_, S, H * 64); dq = torch.zeros_like(q); dk = torch.zeros_like(k); dv = torch.zeros_like(v)
-    ws = torch.zeros(B_, H, S, device=dev)
+    ws = torch.zeros(ops.attn_bwd_ws_floats(B_, H, S, S), device=dev)
     for fn, name, flops in ((lambda: ops.attn_fwd(q, k, v, None, out, lse, B_, H, S, S, 0.125), "attn_fwd", 4 * S * S * 64 * H),
                             (lambda: ops.attn_bwd(q, k, v, None, out, dout, lse, ws, dq, dk, dv, B_, H, S, S, 0.125), "attn_bwd", 10 * S * S * 64 * H)):
         try:

@@ -23,10 +23,10 @@ ao = torch.empty(1, S, D, device=dev, dtype=torch.bfloat16)
 lse = torch.empty(1, H, S, device=dev)
 dout = rnd(1, S, D)
 dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-delta = torch.empty(1, H, S, device=dev)
+delta = torch.empty(ops.attn_bwd_ws_floats(1, H, S, S), device=dev)
 qkv = rnd(R, 3 * D)
-cos = torch.randn(S, D, device=dev)
-sin = torch.randn(S, D, device=dev)
+cos = torch.randn(S, D // 2, device=dev)
+sin = torch.randn(S, D // 2, device=dev)
 for _ in range(n_rep):
     ops.gemm(x, W1, f, M=R, N=4 * D, K=D, bias=b1, epi=ops.EPI_GELU, out2=pre)                       # FFN up
     ops.gemm(f, W2, h, M=R, N=D, K=4 * D, bias=b2, epi=ops.EPI_GATE_RES, res=res, gate_table=tab[5],
