@@ -452,7 +452,9 @@ static int pick_block_n(int M, int N, int nsm, int work_mult, int b_mn, int grou
         int n_tiles = (N + bn - 1) / bn;
         long long tiles = (long long)m_tiles * n_tiles * work_mult;
         long long waves = (tiles + nsm - 1) / nsm;
-        double t = (double)waves * (bn + 24);  // +24: per-tile fixed cost (pipeline fill, epilogue tail)
+        // per-k-block tile time is bounded by operand delivery, ~(128 + bn) rows of 128 B per k-block (measured on B200:
+        // at bn=128 the 1-CTA tile is L2->smem bound, at bn=256 MMA and delivery balance); + a fixed epilogue/fill term
+        double t = (double)waves * ((128 + bn) + 16);
         if (t < best_t - 1e-9) {
             best_t = t;
             best = bn;
