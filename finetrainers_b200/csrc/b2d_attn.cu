@@ -15,6 +15,7 @@
 //   DKV=true : CTA per (key tile j): S^T = K_j Q_i^T, dP^T = V_j dO_i^T, P^T, dS^T -> dV += P^T dO_i, dK += dS^T Q_i
 //   DKV=false: CTA per (query tile i): S = Q_i K_j^T, dP = dO_i V_j^T, dS -> dQ += dS K_j
 // (no atomics, deterministic).
+#include <stdlib.h>
 #include "b2d_internal.h"
 #include "b2d_ptx.cuh"
 
@@ -51,11 +52,14 @@ struct AttnFwdParams {
 };
 
 constexpr int FWD_KV_STAGES = 2;
-constexpr int FWD_SMEM = TILE_BYTES /*Q*/ + FWD_KV_STAGES * 2 * TILE_BYTES /*K,V*/ + 2 * TILE_BYTES /*P*/ + 1024 + 256;
+// 112.25 KB: two CTAs (+1 KB reserved each) must fit the SM's 228 KB, so no alignment slack: the dynamic smem window is
+// declared 1024-byte aligned instead.
+constexpr int FWD_SMEM = TILE_BYTES /*Q*/ + FWD_KV_STAGES * 2 * TILE_BYTES /*K,V*/ + 2 * TILE_BYTES /*P*/ + 256;
 
 __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ uint8_t smem_fwd[];  // no static smem in this kernel: the dynamic window starts 1024-aligned
+    uint8_t* smem = smem_fwd;
+    if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzled tiles need a 1024-byte aligned base
     uint8_t* sQ = smem;
     uint8_t* sKV = sQ + TILE_BYTES;                        // stage s: K at sKV + s*32K, V at +16K
     uint8_t* sP = sKV + FWD_KV_STAGES * 2 * TILE_BYTES;    // 2 chunks of [128 x 64] bf16
@@ -336,6 +340,273 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
 }
 
 // ================================================================================================
+// forward, ping-pong version: ONE CTA per SM owns TWO 128-query tiles (one per softmax warpgroup); K/V tiles are loaded
+// once for both; the MMA warp alternates  S_t(j+1) / P_t V(j)  between the two tiles so that the tensor pipe works on one
+// tile while the other tile's warpgroup exponentiates.
+// ================================================================================================
+constexpr int FPP_STAGES = 3;
+constexpr int FPP_THREADS = 320;
+constexpr int FPP_SMEM = 2 * TILE_BYTES /*Q0,Q1*/ + FPP_STAGES * 2 * TILE_BYTES /*K,V*/ + 2 * 2 * TILE_BYTES /*P0,P1*/ + 1024 + 256;
+
+__global__ void __launch_bounds__(FPP_THREADS, 1) attn_fwd_pp_kernel(const __grid_constant__ AttnFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                                     // [2] tiles
+    uint8_t* sKV = sQ + 2 * TILE_BYTES;                     // stage s: K at +s*32K, V at +16K
+    uint8_t* sPall = sKV + FPP_STAGES * 2 * TILE_BYTES;     // P_t at + t*32K (2 swizzled chunks each)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sPall + 2 * 2 * TILE_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;    // [3]
+    uint64_t* kv_empty = bars + 4;   // [3]
+    uint64_t* s_full = bars + 7;     // [2]
+    uint64_t* p_full = bars + 9;     // [2]
+    uint64_t* pv_done = bars + 11;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 2 * TILE;
+    const int bh = blockIdx.y;
+    const int b = bh / p.H, h = bh % p.H;
+    const int n_kv = (p.Sk + TILE - 1) / TILE;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmQ);
+        tma_prefetch_desc(&p.tmK);
+        tma_prefetch_desc(&p.tmV);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < FPP_STAGES; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&pv_done[i], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;  // S_t at 128*t, O_t at 256 + 64*t
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(q_full, 2 * TILE_BYTES);
+            tma_load_4d(sQ, &p.tmQ, q_full, 0, h, q0, b);
+            tma_load_4d(sQ + TILE_BYTES, &p.tmQ, q_full, 0, h, q0 + TILE, b);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(&kv_empty[stage], phase ^ 1);
+                mbar_expect_tx(&kv_full[stage], 2 * TILE_BYTES);
+                tma_load_4d(sKV + stage * 2 * TILE_BYTES, &p.tmK, &kv_full[stage], 0, h, j * TILE, b);
+                tma_load_4d(sKV + stage * 2 * TILE_BYTES + TILE_BYTES, &p.tmV, &kv_full[stage], 0, h, j * TILE, b);
+                if (++stage == FPP_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+            mbar_wait(q_full, 0);
+            auto issue_s = [&](int t, int j) {
+                const uint32_t aQ = smem_u32(sQ + t * TILE_BYTES);
+                const uint32_t aK = smem_u32(sKV + (j % FPP_STAGES) * 2 * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16(tmem + t * 128, make_sdesc_sw128(aQ + k * 32, 16, 1024), make_sdesc_sw128(aK + k * 32, 16, 1024),
+                             idesc_s, k > 0);
+                umma_commit(&s_full[t]);
+            };
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            issue_s(1, 0);
+            for (int j = 0; j < n_kv; ++j) {
+                const int st = j % FPP_STAGES;
+                const uint32_t aV = smem_u32(sKV + st * 2 * TILE_BYTES + TILE_BYTES);
+                if (j + 1 < n_kv) {
+                    mbar_wait(&kv_full[(j + 1) % FPP_STAGES], (uint32_t)(((j + 1) / FPP_STAGES) & 1));
+                    tc_fence_after();
+                }
+#pragma unroll 1
+                for (int t = 0; t < 2; ++t) {
+                    mbar_wait(&p_full[t], (uint32_t)(j & 1));
+                    tc_fence_after();
+                    const uint32_t aP = smem_u32(sPall + t * 2 * TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        umma_f16(tmem + 256 + t * 64, make_sdesc_sw128(aP + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
+                                 make_sdesc_sw128(aV + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&pv_done[t]);
+                    if (t == 1) umma_commit(&kv_empty[st]);
+                    if (j + 1 < n_kv) issue_s(t, j + 1);  // S_t(j+1): its warpgroup finished reading S_t(j) before p_full
+                }
+            }
+        }
+    } else {
+        const int t = (warp - 2) >> 2;  // which query tile / warpgroup
+        const int qd = warp & 3;
+        const int r = qd * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const uint32_t tS = tmem + t * 128, tO = tmem + 256 + t * 64;
+        uint8_t* sP = sPall + t * 2 * TILE_BYTES;
+        uint64_t* my_s_full = &s_full[t];
+        uint64_t* my_p_full = &p_full[t];
+        uint64_t* my_pv_done = &pv_done[t];
+        float m_run = -INFINITY, l_run = 0.f;
+        const float* kb = p.key_bias ? p.key_bias + (long long)b * p.Sk : nullptr;
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(my_s_full, j & 1);
+            tc_fence_after();
+            const int kv0 = j * TILE;
+            const bool fast = (kb == nullptr) && (kv0 + TILE <= p.Sk);
+            bool done = false;
+            if (fast && j > 0) {
+                mbar_wait(my_pv_done, (j - 1) & 1);
+                tc_fence_after();
+                float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
+                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                const float nm = -m_run;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tS + lane_off + c * 32, v);
+                    tmem_ld_wait();
+                    float pv[32];
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) {
+                        const float a0 = __uint_as_float(v[e]), a1 = __uint_as_float(v[e + 1]);
+                        const float a2 = __uint_as_float(v[e + 2]), a3 = __uint_as_float(v[e + 3]);
+                        t0 = fmaxf(t0, a0); t1 = fmaxf(t1, a1); t2 = fmaxf(t2, a2); t3 = fmaxf(t3, a3);
+                        pv[e] = fast_exp2(fmaf(a0, p.scale_log2, nm));
+                        pv[e + 1] = fast_exp2(fmaf(a1, p.scale_log2, nm));
+                        pv[e + 2] = fast_exp2(fmaf(a2, p.scale_log2, nm));
+                        pv[e + 3] = fast_exp2(fmaf(a3, p.scale_log2, nm));
+                        l0 += pv[e]; l1 += pv[e + 1]; l2 += pv[e + 2]; l3 += pv[e + 3];
+                    }
+                    uint8_t* chunk = sP + (c >> 1) * TILE_BYTES;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 w = make_uint4(pack_bf16x2(pv[u * 8], pv[u * 8 + 1]), pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]),
+                                             pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]), pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]));
+                        *reinterpret_cast<uint4*>(chunk + sw128_off(r, (c & 1) * 4 + u)) = w;
+                    }
+                }
+                const float mxo = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) * p.scale_log2;
+                if (!__any_sync(0xffffffffu, (mxo - m_run) > 8.0f)) {
+                    l_run += (l0 + l1) + (l2 + l3);
+                    done = true;
+                }
+            }
+            if (!done) {
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tS + lane_off + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int col = kv0 + c * 32 + e;
+                        float x = __uint_as_float(v[e]) * p.scale_log2;
+                        if (kb) x += kb[min(col, p.Sk - 1)] * LOG2E;
+                        x = col < p.Sk ? x : -INFINITY;
+                        mx = fmaxf(mx, x);
+                    }
+                }
+                float m_use = m_run;
+                if (j == 0) {
+                    m_use = mx;
+                } else {
+                    const bool need = (mx - m_run) > 8.0f;
+                    mbar_wait(my_pv_done, (j - 1) & 1);
+                    tc_fence_after();
+                    if (__any_sync(0xffffffffu, need)) {
+                        if (need) m_use = mx;
+                        const float alpha = fast_exp2(m_run - m_use);
+                        l_run *= alpha;
+#pragma unroll 1
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t v[32];
+                            tmem_ld32(tO + lane_off + c * 32, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+                            tmem_st32(tO + lane_off + c * 32, v);
+                        }
+                        tmem_st_wait();
+                    }
+                }
+                m_run = m_use;
+                float l0 = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tS + lane_off + c * 32, v);
+                    tmem_ld_wait();
+                    float pv[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int col = kv0 + c * 32 + e;
+                        float x = __uint_as_float(v[e]) * p.scale_log2 - m_use;
+                        if (kb) x += kb[min(col, p.Sk - 1)] * LOG2E;
+                        float pe = col < p.Sk ? fast_exp2(x) : 0.f;
+                        pv[e] = pe;
+                        l0 += pe;
+                    }
+                    uint8_t* chunk = sP + (c >> 1) * TILE_BYTES;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 w = make_uint4(pack_bf16x2(pv[u * 8], pv[u * 8 + 1]), pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]),
+                                             pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]), pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]));
+                        *reinterpret_cast<uint4*>(chunk + sw128_off(r, (c & 1) * 4 + u)) = w;
+                    }
+                }
+                l_run += l0;
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(my_p_full);
+        }
+        mbar_wait(my_pv_done, (n_kv - 1) & 1);
+        tc_fence_after();
+        const int qrow = q0 + t * TILE + r;
+        const float inv_l = 1.f / l_run;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tO + lane_off + c * 32, v);
+            tmem_ld_wait();
+            if (qrow < p.Sq) {
+                __nv_bfloat16* o = p.out + ((long long)b * p.Sq + qrow) * (p.H * HD) + h * HD + c * 32;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint4 w = make_uint4(
+                        pack_bf16x2(__uint_as_float(v[u * 8]) * inv_l, __uint_as_float(v[u * 8 + 1]) * inv_l),
+                        pack_bf16x2(__uint_as_float(v[u * 8 + 2]) * inv_l, __uint_as_float(v[u * 8 + 3]) * inv_l),
+                        pack_bf16x2(__uint_as_float(v[u * 8 + 4]) * inv_l, __uint_as_float(v[u * 8 + 5]) * inv_l),
+                        pack_bf16x2(__uint_as_float(v[u * 8 + 6]) * inv_l, __uint_as_float(v[u * 8 + 7]) * inv_l));
+                    *reinterpret_cast<uint4*>(o + u * 8) = w;
+                }
+            }
+        }
+        if (qrow < p.Sq) p.lse[((long long)b * p.H + h) * p.Sq + qrow] = m_run * LN2 + logf(l_run);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// ================================================================================================
 // backward
 // ================================================================================================
 // delta[b,h,q] = sum_d out[b,q,h,d] * dout[b,q,h,d]     (8 lanes per head-row)
@@ -377,6 +648,7 @@ struct AttnBwdParams {
     float* acc1;                         // split mode (gridDim.z > 1): fp32 accumulators, atomically added, same layout
     float* acc2;
     int y_per_split;                     // streamed tiles per z-slice
+    int dbg;                             // timing experiments only (B2D_ATTN_DBG): 1 no exp, 2 no smem stores, 4 no col LDS, 8 no tmem ld
     int B, H, Sq, Sk;
     float scale, scale_log2;
 };
@@ -648,6 +920,298 @@ __global__ void __launch_bounds__(ATT_THREADS, (TY == 64 ? 2 : 1)) attn_bwd_kern
     }
 }
 
+// ================================================================================================
+// backward, ping-pong version: ONE CTA per SM, two consumer warpgroups alternate streamed tiles while the MMA warp runs
+// one tile ahead (S/dP and P/dS double-buffered), so tensor pipe, MUFU and the FMA pipe overlap inside the CTA:
+//     MMA :  SdP(0)  SdP(1)  dVdK(0)  SdP(2)  dVdK(1)  SdP(3)  dVdK(2) ...
+//     WG0 :          [exp,dS](0)              [exp,dS](2)      ...
+//     WG1 :                   [exp,dS](1)              [exp,dS](3)
+// ================================================================================================
+constexpr int PP_TY = 64;
+constexpr int PP_STAGES = 3;
+constexpr int PP_THREADS = 320;                       // TMA warp, MMA warp, 2 x 4 consumer warps
+constexpr int PP_Y_BYTES = PP_TY * HD * 2;            // 8 KB
+constexpr int PP_PS_BYTES = TILE * PP_TY * 2;         // 16 KB
+constexpr int PP_SMEM = 2 * TILE_BYTES + PP_STAGES * 2 * PP_Y_BYTES + 4 * PP_PS_BYTES + PP_STAGES * 2 * PP_TY * 4 + 1024 + 256;
+
+template <bool DKV>
+__global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid_constant__ AttnBwdParams p) {
+    constexpr int TY = PP_TY;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sX1 = smem;
+    uint8_t* sX2 = sX1 + TILE_BYTES;
+    uint8_t* sY = sX2 + TILE_BYTES;                         // stage s: Y1 at +s*2*Y_BYTES, Y2 right after
+    uint8_t* sP = sY + PP_STAGES * 2 * PP_Y_BYTES;          // P^T buffers [2]
+    uint8_t* sDS = sP + 2 * PP_PS_BYTES;                    // dS buffers [2]
+    float* sColA = reinterpret_cast<float*>(sDS + 2 * PP_PS_BYTES);  // [stages][TY]
+    float* sColD = sColA + PP_STAGES * TY;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sColD + PP_STAGES * TY);
+    uint64_t* x_full = bars;
+    uint64_t* y_full = bars + 1;     // [3]
+    uint64_t* y_empty = bars + 4;    // [3]
+    uint64_t* s_full = bars + 7;     // [2]
+    uint64_t* ds_full = bars + 9;    // [2]
+    uint64_t* mm_done = bars + 11;   // [2]
+    uint64_t* all_done = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x0 = blockIdx.x * TILE;
+    const int bh = blockIdx.y;
+    const int b = bh / p.H, h = bh % p.H;
+    const int rowsX = DKV ? p.Sk : p.Sq;
+    const int rowsY = DKV ? p.Sq : p.Sk;
+    const int n_y_all = (rowsY + TY - 1) / TY;
+    const int y0 = blockIdx.z * p.y_per_split;
+    const int y1 = min(n_y_all, y0 + p.y_per_split);
+    const int n_y = y1 - y0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmX1);
+        tma_prefetch_desc(&p.tmX2);
+        tma_prefetch_desc(&p.tmY1);
+        tma_prefetch_desc(&p.tmY2);
+        mbar_init(x_full, 1);
+        for (int i = 0; i < PP_STAGES; ++i) {
+            mbar_init(&y_full[i], 1);
+            mbar_init(&y_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&ds_full[i], 128);
+            mbar_init(&mm_done[i], 1);
+        }
+        mbar_init(all_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    // S[b] at 128*b, dP[b] at 128*b + 64, out1 at 256, out2 at 320
+    const uint32_t tO1 = tmem + 256, tO2 = tmem + 320;
+
+    if (warp == 0) {
+        if (elect_one() && n_y > 0) {
+            mbar_expect_tx(x_full, 2 * TILE_BYTES);
+            tma_load_4d(sX1, &p.tmX1, x_full, 0, h, x0, b);
+            tma_load_4d(sX2, &p.tmX2, x_full, 0, h, x0, b);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < n_y; ++it) {
+                const int i = y0 + it;
+                mbar_wait(&y_empty[stage], phase ^ 1);
+                const bool colvec = DKV && ((i + 1) * TY <= rowsY) && ((rowsY & 3) == 0);
+                mbar_expect_tx(&y_full[stage], 2 * PP_Y_BYTES + (colvec ? 2 * TY * 4 : 0));
+                tma_load_4d(sY + stage * 2 * PP_Y_BYTES, &p.tmY1, &y_full[stage], 0, h, i * TY, b);
+                tma_load_4d(sY + stage * 2 * PP_Y_BYTES + PP_Y_BYTES, &p.tmY2, &y_full[stage], 0, h, i * TY, b);
+                if (colvec) {
+                    const long long off = ((long long)b * p.H + h) * p.Sq + (long long)i * TY;
+                    bulk_load_1d(sColA + stage * TY, p.nlse2 + off, TY * 4, &y_full[stage]);
+                    bulk_load_1d(sColD + stage * TY, p.delta + off, TY * 4, &y_full[stage]);
+                }
+                if (++stage == PP_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one() && n_y > 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, TY, 0, 0);
+            constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+            mbar_wait(x_full, 0);
+            const uint32_t aX1 = smem_u32(sX1), aX2 = smem_u32(sX2);
+            auto issue_sdp = [&](int it) {  // S and dP of local tile `it` into TMEM buffer it&1
+                const int st = it % PP_STAGES;
+                mbar_wait(&y_full[st], (uint32_t)((it / PP_STAGES) & 1));
+                tc_fence_after();
+                const uint32_t aY1 = smem_u32(sY + st * 2 * PP_Y_BYTES), aY2 = aY1 + PP_Y_BYTES;
+                const uint32_t tS = tmem + (it & 1) * 128, tDP = tS + 64;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16(tS, make_sdesc_sw128(aX1 + k * 32, 16, 1024), make_sdesc_sw128(aY1 + k * 32, 16, 1024),
+                             idesc_s, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16(tDP, make_sdesc_sw128(aX2 + k * 32, 16, 1024), make_sdesc_sw128(aY2 + k * 32, 16, 1024),
+                             idesc_s, k > 0);
+                umma_commit(&s_full[it & 1]);
+            };
+            issue_sdp(0);
+            for (int it = 0; it < n_y; ++it) {
+                if (it + 1 < n_y) issue_sdp(it + 1);  // runs one tile ahead of the consumers
+                const int bsel = it & 1;
+                const int st = it % PP_STAGES;
+                mbar_wait(&ds_full[bsel], (uint32_t)((it >> 1) & 1));
+                tc_fence_after();
+                const uint32_t aY1 = smem_u32(sY + st * 2 * PP_Y_BYTES), aY2 = aY1 + PP_Y_BYTES;
+                const uint32_t aP = smem_u32(sP + bsel * PP_PS_BYTES), aDS = smem_u32(sDS + bsel * PP_PS_BYTES);
+                if (DKV) {
+#pragma unroll
+                    for (int k = 0; k < TY / 16; ++k)  // out1 (dV) += P^T . dO_i   (Y2 as MN-major B)
+                        umma_f16(tO1, make_sdesc_sw128(aP + k * 32, 16, 1024), make_sdesc_sw128(aY2 + k * 2048, 8192, 1024),
+                                 idesc_o, (it > 0 || k > 0) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < TY / 16; ++k)  // out2 += dS . Y1   (Y1 as MN-major B)
+                    umma_f16(tO2, make_sdesc_sw128(aDS + k * 32, 16, 1024), make_sdesc_sw128(aY1 + k * 2048, 8192, 1024),
+                             idesc_o, (it > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&y_empty[st]);
+                umma_commit(&mm_done[bsel]);
+            }
+            umma_commit(all_done);
+        }
+    } else {
+        const int wg = (warp - 2) >> 2;           // consumer warpgroup 0 / 1 handles local tiles it = wg, wg+2, ...
+        const int qd = warp & 3;
+        const int r = qd * 32 + lane;
+        const int tid128 = ((warp - 2) & 3) * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const int xrow = x0 + r;
+        const bool row_ok = xrow < rowsX;
+        const long long bhoff = (long long)b * p.H + h;
+        float rowA, rowD = 0.f;
+        if (DKV) {
+            rowA = (p.key_bias && row_ok) ? p.key_bias[(long long)b * p.Sk + xrow] * LOG2E : 0.f;
+        } else {
+            rowA = row_ok ? -p.lse[bhoff * p.Sq + xrow] * LOG2E : 0.f;
+            rowD = row_ok ? p.delta[bhoff * p.Sq + xrow] : 0.f;
+        }
+        if (!row_ok) rowA = -INFINITY;
+        uint8_t* myP = sP + wg * PP_PS_BYTES;
+        uint8_t* myDS = sDS + wg * PP_PS_BYTES;
+        const uint32_t tS = tmem + wg * 128, tDP = tS + 64;
+        for (int it = wg; it < n_y; it += 2) {
+            const int i = y0 + it;
+            const int st = it % PP_STAGES;
+            const int t = it >> 1;  // this warpgroup's own tile counter
+            float* cA = sColA + st * TY;
+            float* cD = sColD + st * TY;
+            const bool full_tile = (i + 1) * TY <= rowsY;
+            const bool col_by_copy = DKV && full_tile && ((rowsY & 3) == 0);
+            const bool no_col = !DKV && full_tile && (p.key_bias == nullptr);
+            if (!col_by_copy && !no_col) {
+                if (tid128 < TY) {
+                    const int ycol = i * TY + tid128;
+                    const bool ok = ycol < rowsY;
+                    if (DKV) {
+                        cA[tid128] = ok ? -p.lse[bhoff * p.Sq + ycol] * LOG2E : -INFINITY;
+                        cD[tid128] = ok ? p.delta[bhoff * p.Sq + ycol] : 0.f;
+                    } else {
+                        cA[tid128] = ok ? (p.key_bias ? p.key_bias[(long long)b * p.Sk + ycol] * LOG2E : 0.f) : -INFINITY;
+                        cD[tid128] = 0.f;
+                    }
+                }
+                named_bar_sync(1 + wg, 128);
+            }
+            if (col_by_copy) mbar_wait(&y_full[st], (uint32_t)((it / PP_STAGES) & 1));
+            mbar_wait(&s_full[wg], (uint32_t)(t & 1));
+            tc_fence_after();
+            if (t > 0) {  // this warpgroup's P/dS buffers were last read by the MMAs of its previous tile
+                mbar_wait(&mm_done[wg], (uint32_t)((t - 1) & 1));
+                tc_fence_after();
+            }
+#pragma unroll 1
+            for (int c = 0; c < TY / 32; ++c) {
+                uint32_t sv[32], dv[32];
+                if (!(p.dbg & 8)) {
+                    tmem_ld32(tS + lane_off + c * 32, sv);
+                    tmem_ld32(tDP + lane_off + c * 32, dv);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) { sv[e] = 0x3c000000u + e + it; dv[e] = 0x3c100000u + e; }
+                }
+                float pe[32], ds[32];
+                if (no_col || (p.dbg & 4)) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        float x = fmaf(__uint_as_float(sv[e]), p.scale_log2, rowA);
+                        float pp = (p.dbg & 1) ? x : fast_exp2(x);
+                        pe[e] = pp;
+                        ds[e] = pp * (__uint_as_float(dv[e]) - rowD);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int cc = c * 32 + e;
+                        float x = fmaf(__uint_as_float(sv[e]), p.scale_log2, rowA + cA[cc]);
+                        float pp = (p.dbg & 1) ? x : fast_exp2(x);
+                        pe[e] = pp;
+                        ds[e] = pp * (__uint_as_float(dv[e]) - (DKV ? cD[cc] : rowD));
+                    }
+                }
+                if (p.dbg & 2) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) acc += pe[e] + ds[e];
+                    if (acc == 123.456f) *reinterpret_cast<float*>(myDS) = acc;  // keep the math alive
+                    continue;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t off = sw128_off(r, c * 4 + u);
+                    if (DKV) {
+                        uint4 w = make_uint4(pack_bf16x2(pe[u * 8], pe[u * 8 + 1]), pack_bf16x2(pe[u * 8 + 2], pe[u * 8 + 3]),
+                                             pack_bf16x2(pe[u * 8 + 4], pe[u * 8 + 5]), pack_bf16x2(pe[u * 8 + 6], pe[u * 8 + 7]));
+                        *reinterpret_cast<uint4*>(myP + off) = w;
+                    }
+                    uint4 w2 = make_uint4(pack_bf16x2(ds[u * 8], ds[u * 8 + 1]), pack_bf16x2(ds[u * 8 + 2], ds[u * 8 + 3]),
+                                          pack_bf16x2(ds[u * 8 + 4], ds[u * 8 + 5]), pack_bf16x2(ds[u * 8 + 6], ds[u * 8 + 7]));
+                    *reinterpret_cast<uint4*>(myDS + off) = w2;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&ds_full[wg]);
+        }
+        // ---- epilogue: DKV: warpgroup 0 writes dV (out1), warpgroup 1 writes dK (out2); dQ: each takes 32 columns
+        if (n_y > 0) {
+            mbar_wait(all_done, 0);
+            tc_fence_after();
+            const long long ro = (bhoff * rowsX + xrow) * HD;
+#pragma unroll 1
+            for (int piece = 0; piece < 2; ++piece) {
+                int which, c;
+                if (DKV) { which = wg; c = piece; } else { which = 1; c = wg; if (piece == 1) break; }
+                const uint32_t tacc = which == 0 ? tO1 : tO2;
+                const float osc = which == 0 ? 1.f : p.scale;
+                float* facc = which == 0 ? p.acc1 : p.acc2;
+                uint32_t v[32];
+                tmem_ld32(tacc + lane_off + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * osc);
+                if (row_ok) {
+                    if (gridDim.z > 1) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) atomicAdd(facc + ro + c * 32 + e, __uint_as_float(v[e]));
+                    } else {
+                        __nv_bfloat16* dst = (which == 0 ? p.out1 : p.out2) + ro;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            uint4 w = make_uint4(pack_bf16x2(__uint_as_float(v[u * 8]), __uint_as_float(v[u * 8 + 1])),
+                                                 pack_bf16x2(__uint_as_float(v[u * 8 + 2]), __uint_as_float(v[u * 8 + 3])),
+                                                 pack_bf16x2(__uint_as_float(v[u * 8 + 4]), __uint_as_float(v[u * 8 + 5])),
+                                                 pack_bf16x2(__uint_as_float(v[u * 8 + 6]), __uint_as_float(v[u * 8 + 7])));
+                            *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = w;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
     long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
@@ -704,9 +1268,16 @@ extern "C" int b2d_attn_fwd(const void* q, const void* k, const void* v, const f
     p.lse = lse;
     p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
     p.scale_log2 = scale * LOG2E;
+    static const bool use_pp = []() { const char* e = getenv("B2D_ATTN_FWD"); return !(e && e[0] == 'c'); }();
     if ((rc = set_smem((const void*)attn_fwd_kernel, FWD_SMEM, "attn_fwd"))) return rc;
-    dim3 grid((Sq + TILE - 1) / TILE, B * H);
-    attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    if ((rc = set_smem((const void*)attn_fwd_pp_kernel, FPP_SMEM, "attn_fwd_pp"))) return rc;
+    if (use_pp && Sq > TILE) {
+        dim3 grid((Sq + 2 * TILE - 1) / (2 * TILE), B * H);
+        attn_fwd_pp_kernel<<<grid, FPP_THREADS, FPP_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    } else {
+        dim3 grid((Sq + TILE - 1) / TILE, B * H);
+        attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    }
     B2D_CHECK_LAUNCH("attn_fwd");
     return 0;
 }
@@ -739,15 +1310,19 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
     p.key_bias = key_bias; p.lse = lse; p.delta = delta_ws; p.nlse2 = delta_ws + (long long)B * H * Sq;
     p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
     p.scale = scale; p.scale_log2 = scale * LOG2E;
+    { const char* e = getenv("B2D_ATTN_DBG"); p.dbg = e ? atoi(e) : 0; }
     // dK, dV.  With few key tiles (cross attention: Sk = 128 -> B*H CTAs) the query range is split over gridDim.z and
     // the partial dK/dV are accumulated with fp32 atomics in the tail of delta_ws, then rounded to bf16.
     p.tmX1 = mK; p.tmX2 = mV; p.tmY1 = mQy; p.tmY2 = mdOy;
     p.out1 = (__nv_bfloat16*)dv; p.out2 = (__nv_bfloat16*)dk;
+    static const bool use_pp = []() { const char* e = getenv("B2D_ATTN_BWD"); return !(e && e[0] == 'c'); }();
     const int n_yq = (Sq + TY - 1) / TY;
     const int kv_ctas = ((Sk + TILE - 1) / TILE) * B * H;
     int splits = 1;
     if (kv_ctas < 96 && Sk <= 512 && n_yq >= 8) splits = min(min(8, n_yq / 4), (2 * 148 + kv_ctas - 1) / kv_ctas);
     if ((rc = set_smem((const void*)attn_bwd_kernel<true, TY>, BwdCfg<TY>::SMEM, "attn_bwd_dkv"))) return rc;
+    if ((rc = set_smem((const void*)attn_bwd_pp_kernel<true>, PP_SMEM, "attn_bwd_pp_dkv"))) return rc;
+    if ((rc = set_smem((const void*)attn_bwd_pp_kernel<false>, PP_SMEM, "attn_bwd_pp_dq"))) return rc;
     p.y_per_split = (n_yq + splits - 1) / splits;
     if (splits > 1) {
         const long long n_kv = (long long)B * H * Sk * HD;
@@ -755,13 +1330,19 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
         p.acc2 = p.acc1 + n_kv;
         cudaError_t e = cudaMemsetAsync(p.acc1, 0, 2 * n_kv * sizeof(float), st);
         if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "attn_bwd memset: %s", cudaGetErrorString(e));
-        attn_bwd_kernel<true, TY><<<dim3((Sk + TILE - 1) / TILE, B * H, splits), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
+        if (use_pp)
+            attn_bwd_pp_kernel<true><<<dim3((Sk + TILE - 1) / TILE, B * H, splits), PP_THREADS, PP_SMEM, st>>>(p);
+        else
+            attn_bwd_kernel<true, TY><<<dim3((Sk + TILE - 1) / TILE, B * H, splits), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
         B2D_CHECK_LAUNCH("attn_bwd_dkv(split)");
         f32_to_bf16_kernel<<<(unsigned)((n_kv / 4 + 255) / 256), 256, 0, st>>>(p.acc1, (__nv_bfloat16*)dv, n_kv);
         f32_to_bf16_kernel<<<(unsigned)((n_kv / 4 + 255) / 256), 256, 0, st>>>(p.acc2, (__nv_bfloat16*)dk, n_kv);
         B2D_CHECK_LAUNCH("attn_bwd_dkv(convert)");
     } else {
-        attn_bwd_kernel<true, TY><<<dim3((Sk + TILE - 1) / TILE, B * H), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
+        if (use_pp)
+            attn_bwd_pp_kernel<true><<<dim3((Sk + TILE - 1) / TILE, B * H), PP_THREADS, PP_SMEM, st>>>(p);
+        else
+            attn_bwd_kernel<true, TY><<<dim3((Sk + TILE - 1) / TILE, B * H), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
         B2D_CHECK_LAUNCH("attn_bwd_dkv");
     }
     p.acc1 = p.acc2 = nullptr;
@@ -770,7 +1351,10 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
     p.out1 = nullptr; p.out2 = (__nv_bfloat16*)dq;
     p.y_per_split = (Sk + TY - 1) / TY;
     if ((rc = set_smem((const void*)attn_bwd_kernel<false, TY>, BwdCfg<TY>::SMEM, "attn_bwd_dq"))) return rc;
-    attn_bwd_kernel<false, TY><<<dim3((Sq + TILE - 1) / TILE, B * H), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
+    if (use_pp)
+        attn_bwd_pp_kernel<false><<<dim3((Sq + TILE - 1) / TILE, B * H), PP_THREADS, PP_SMEM, st>>>(p);
+    else
+        attn_bwd_kernel<false, TY><<<dim3((Sq + TILE - 1) / TILE, B * H), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
     B2D_CHECK_LAUNCH("attn_bwd_dq");
     return 0;
 }

@@ -236,6 +236,7 @@ class B200LTXTransformer(nn.Module):
         self._blk = []
         # flat fp32 LoRA master + grad (padded rank) and bf16 operand copy
         per_blk = (8 * rp * d) * 2 if r else 0  # A:[3rp+rp+rp+2rp+rp, d] ; B:[(3+1+1+2+1) d, rp]
+        self._per_blk = per_blk
         nl = cfg.num_layers
         if r:
             self.lora_flat = torch.zeros(nl * per_blk, dtype=torch.float32, device=dev)
@@ -347,13 +348,17 @@ class B200LTXTransformer(nn.Module):
         if rp:
             z("u_qkv", nl, R, 3 * rp); z("u_o", nl, R, rp); z("u_q2", nl, R, rp); z("u_kv2", nl, RL, 2 * rp)
             z("u_o2", nl, R, rp)
-            z("du_big", R, 3 * rp); z("du_txt", RL, 2 * rp)
+            # per-block copies of every adapter's output gradient dy and of du = s*dy*B: the weight gradients dA/dB of all
+            # 28 blocks are computed at the END of backward as a handful of block-batched GEMMs (1.9 GB at B=1)
+            z("dy_o2", nl, R, d); z("dy_q2", nl, R, d); z("dy_kv2", nl, RL, 2 * d); z("dy_o", nl, R, d)
+            z("dy_qkv", nl, R, 3 * d)
+            z("du_o2", nl, R, rp); z("du_q2", nl, R, rp); z("du_kv2", nl, RL, 2 * rp); z("du_o", nl, R, rp)
+            z("du_qkv", nl, R, 3 * rp)
         # scratch shared by all blocks
         z("n2", R, d); z("f", R, cfg.ffn_mult * d); z("y", R, d); z("pred", R, cfg.out_channels)
         z("dh", R, d); z("g", R, d); z("dwide", R, cfg.ffn_mult * d); z("dn", R, d); z("da", R, d)
         z("dqh", B, H, S, 64); z("dkh", B, H, S, 64); z("dvh", B, H, S, 64)
         z("dk2h", B, H, L, 64); z("dv2h", B, H, L, 64)
-        z("dqkv", R, 3 * d); z("dq2", R, d); z("dkv2", RL, 2 * d)
         z("delta", max(ops.attn_bwd_ws_floats(B, H, S, S), ops.attn_bwd_ws_floats(B, H, S, L)), kw=f32)
         self._ws[key] = ws
         return ws
@@ -501,23 +506,48 @@ class B200LTXTransformer(nn.Module):
         per = -(-kb // s)
         return -(-kb // per)
 
-    def _lora_bwd(self, dy, x, u, du, e, g, M, N, K, n_ad):
-        """dy [M,N] (N = n_ad*Nj), x [M,K], u [M,n_ad*rp] (already scaled).  Fills du, accumulates gA/gB."""
+    def _lora_du(self, dy, du, e, g, M, N, n_ad):
+        """du_j = s * dy_j B_j for the n_ad adapters packed in dy [M, N] -> du [M, n_ad*rp]."""
         rp = self.rpad
         Nj = N // n_ad
-        kb = -(-M // 64)
-        du = du.view(-1)[:M * n_ad * rp].view(M, n_ad * rp)
-        # du_j = s * dy_j B_j
         ops.gemm(dy, e["Bb_" + g], du, M=M, N=rp, K=Nj, b_mn=True, batch=n_ad, a_boff=(0, Nj), b_boff=(Nj, 0),
                  c_boff=rp, ldc=n_ad * rp, alpha=self.lora_scaling, tag="lora_du")
-        # dB_j += dy_j^T u_j
-        ops.gemm(dy, u, e["gB_" + g], M=Nj, N=rp, K=M, a_mn=True, b_mn=True, batch=n_ad, a_boff=(0, Nj), b_boff=(0, rp),
-                 c_boff=Nj * rp, ldc=rp, epi=ops.EPI_F32_ATOMIC, block_n=64 if rp == 64 else 128, tag="lora_dB",
-                 splits=self._splits(-(-Nj // 128) * n_ad * (rp // (64 if rp == 64 else 128)), kb))
-        # dA += du^T x   (computed as (x^T du)^T)
-        ops.gemm(x, du, e["gA_" + g], M=K, N=n_ad * rp, K=M, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC_T, ldc=K,
-                 block_n=64, tag="lora_dA", splits=self._splits(-(-K // 128) * (n_ad * rp // 64), kb))
         return du
+
+    def _lora_wgrads_all(self, ws, R, RL):
+        """dA / dB of every adapter of every block: 13 block-batched split-free GEMMs at the end of backward
+        (dB_j += dy_j^T u_j ;  dA += du^T x computed as (x^T du)^T), accumulating into the flat fp32 gradient buffer."""
+        cfg = self.cfg
+        d, nl, rp, pb = cfg.inner_dim, cfg.num_layers, self.rpad, self._per_blk
+        e0 = self._blk[0]
+        # kv2 has no dX consumer, so its du is also produced here, block-batched per adapter
+        for j in range(2):
+            ops.gemm(ws["dy_kv2"].view(nl * RL, 2 * d)[:, j * d:], e0["Bb_kv2"][j * d:], ws["du_kv2"].view(nl * RL, 2 * rp)[:, j * rp:],
+                     M=RL, N=rp, K=d, lda=2 * d, ldb=rp, ldc=2 * rp, b_mn=True, batch=nl, a_boff=(RL, 0), b_boff=(pb // rp, 0),
+                     c_boff=RL * 2 * rp, alpha=self.lora_scaling, tag="lora_du")
+        groups = (("qkv", ws["dy_qkv"], ws["n1"], ws["u_qkv"], ws["du_qkv"], 3, R, R),
+                  ("o", ws["dy_o"], ws["ao"], ws["u_o"], ws["du_o"], 1, R, R),
+                  ("q2", ws["dy_q2"], ws["h1"], ws["u_q2"], ws["du_q2"], 1, R, R),
+                  ("kv2", ws["dy_kv2"], ws["enc"], ws["u_kv2"], ws["du_kv2"], 2, RL, 0),
+                  ("o2", ws["dy_o2"], ws["ao2"], ws["u_o2"], ws["du_o2"], 1, R, R))
+        for g, dy, x, u, du, n_ad, M, x_stride in groups:
+            N = n_ad * d
+            dy2, u2, du2 = dy.view(nl * M, N), u.view(nl * M, n_ad * rp), du.view(nl * M, n_ad * rp)
+            x2 = x.view(-1, d)
+            # the contraction runs over the M token rows of ONE block: stacking blocks along that axis is only legal when
+            # M is a whole number of 64-row k-blocks (otherwise the k-tail would read the next block's rows, not zeros)
+            if M % 64 == 0:
+                spans = [(0, nl)]
+            else:
+                spans = [(l, 1) for l in range(nl)]
+            for (l0, nb) in spans:
+                for j in range(n_ad):
+                    ops.gemm(dy2[l0 * M:, j * d:], u2[l0 * M:, j * rp:], self._blk[l0]["gB_" + g][j * d:], M=d, N=rp, K=M,
+                             lda=N, ldb=n_ad * rp, ldc=rp, a_mn=True, b_mn=True, batch=nb, a_boff=(M, 0), b_boff=(M, 0),
+                             c_boff=pb, epi=ops.EPI_F32_ATOMIC, block_n=64 if rp == 64 else 128, tag="lora_dB")
+                ops.gemm(x2[l0 * x_stride:], du2[l0 * M:], self._blk[l0]["gA_" + g], M=d, N=n_ad * rp, K=M, lda=d,
+                         ldb=n_ad * rp, ldc=d, a_mn=True, b_mn=True, batch=nb, a_boff=(x_stride, 0), b_boff=(M, 0),
+                         c_boff=pb, epi=ops.EPI_F32_ATOMIC_T, block_n=64, tag="lora_dA")
 
     def _backward_impl(self, dpred):
         cfg = self.cfg
@@ -545,45 +575,46 @@ class B200LTXTransformer(nn.Module):
         for l in range(nl - 1, -1, -1):
             e = self._blk[l]
             sst = e["sst"]
+            dh2, dq2, dkv2, dyo, dqkv = ws["dy_o2"][l], ws["dy_q2"][l], ws["dy_kv2"][l], ws["dy_o"][l], ws["dy_qkv"][l]
             # ---- FFN: dfp = (g W2) * gelu'(pre) ; dn2 = dfp W1 ; dh2 = dh + norm_bwd(dn2; h2, scale_mlp=row 4)
             ops.gemm(g, e["W2"], ws["dwide"], M=R, N=cfg.ffn_mult * d, K=d, b_mn=True, epi=ops.EPI_MUL_DGELU,
                      aux=ws["ffpre"][l])
             ops.gemm(ws["dwide"], e["W1"], ws["dn"], M=R, N=d, K=cfg.ffn_mult * d, b_mn=True)
-            ops.norm_modulate_bwd(ws["dn"], ws["h2"][l], dh, dh, sst[4], temb[:, 4 * d:], 6 * d, R, d, S, cfg.norm_eps)
-            # ---- cross attention out-proj (no gate): da2 = dh W_o2 + du A ; LoRA grads
-            du = self._lora_bwd(dh, ws["ao2"][l], ws["u_o2"][l], ws["du_big"], e, "o2", R, d, d, 1)
-            ops.gemm(dh, e["Wo2"], ws["da"], M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_o2"], K2=rp)
+            ops.norm_modulate_bwd(ws["dn"], ws["h2"][l], dh, dh2, sst[4], temb[:, 4 * d:], 6 * d, R, d, S, cfg.norm_eps)
+            # ---- cross attention out-proj (no gate): da2 = dh2 W_o2 + du A
+            du = self._lora_du(dh2, ws["du_o2"][l], e, "o2", R, d, 1)
+            ops.gemm(dh2, e["Wo2"], ws["da"], M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_o2"], K2=rp)
             ops.attn_bwd(ws["q2h"][l], ws["k2h"][l], ws["v2h"][l], key_bias, ws["ao2"][l], ws["da"], ws["lse2"][l],
                          ws["delta"], ws["dqh"], ws["dk2h"], ws["dv2h"], B, H, S, L, scale)
-            ops.qknorm_rope_bwd(ws["dqh"], ws["q2"][l], d, 0, e["nq2"], None, None, ws["dq2"], d, 0, B, S, H, True,
+            ops.qknorm_rope_bwd(ws["dqh"], ws["q2"][l], d, 0, e["nq2"], None, None, dq2, d, 0, B, S, H, True,
                                 cfg.qk_norm_eps)
-            ops.qknorm_rope_bwd(ws["dk2h"], ws["kv2"][l], 2 * d, 0, e["nk2"], None, None, ws["dkv2"], 2 * d, 0, B, L, H,
+            ops.qknorm_rope_bwd(ws["dk2h"], ws["kv2"][l], 2 * d, 0, e["nk2"], None, None, dkv2, 2 * d, 0, B, L, H,
                                 True, cfg.qk_norm_eps)
-            ops.qknorm_rope_bwd(ws["dv2h"], ws["kv2"][l], 2 * d, d, None, None, None, ws["dkv2"], 2 * d, d, B, L, H, False,
+            ops.qknorm_rope_bwd(ws["dv2h"], ws["kv2"][l], 2 * d, d, None, None, None, dkv2, 2 * d, d, B, L, H, False,
                                 cfg.qk_norm_eps)
-            self._lora_bwd(ws["dkv2"], ws["enc"], ws["u_kv2"][l], ws["du_txt"], e, "kv2", RL, 2 * d, d, 2)
-            du = self._lora_bwd(ws["dq2"], ws["h1"][l], ws["u_q2"][l], ws["du_big"], e, "q2", R, d, d, 1)
-            # dh1 = dh2 + dq2 W_q2 + du A ; g = dh1 * gate_msa (row 2)
-            ops.gemm(ws["dq2"], e["Wq2"], dh, M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_q2"], K2=rp,
-                     epi=ops.EPI_GATE_RES, res=dh, gate2_table=sst[2], gate2_temb=temb[:, 2 * d:], out2=g,
+            du = self._lora_du(dq2, ws["du_q2"][l], e, "q2", R, d, 1)
+            # dh1 = dh2 + dq2 W_q2 + du A ; gated copy (gate_msa, row 2) = dy of the self-attention out-proj
+            ops.gemm(dq2, e["Wq2"], dh, M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_q2"], K2=rp,
+                     epi=ops.EPI_GATE_RES, res=dh2, gate2_table=sst[2], gate2_temb=temb[:, 2 * d:], out2=dyo,
                      temb_stride=6 * d, rows_per_sample=S)
             # ---- self attention out-proj (gated): dattn = g W_o + du A
-            du = self._lora_bwd(g, ws["ao"][l], ws["u_o"][l], ws["du_big"], e, "o", R, d, d, 1)
-            ops.gemm(g, e["Wo"], ws["da"], M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_o"], K2=rp)
+            du = self._lora_du(dyo, ws["du_o"][l], e, "o", R, d, 1)
+            ops.gemm(dyo, e["Wo"], ws["da"], M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_o"], K2=rp)
             ops.attn_bwd(ws["qh"][l], ws["kh"][l], ws["vh"][l], None, ws["ao"][l], ws["da"], ws["lse"][l], ws["delta"],
                          ws["dqh"], ws["dkh"], ws["dvh"], B, H, S, S, scale)
-            ops.qknorm_rope_bwd(ws["dqh"], ws["qkv"][l], 3 * d, 0, e["nq1"], cos, sin, ws["dqkv"], 3 * d, 0, B, S, H, True,
+            ops.qknorm_rope_bwd(ws["dqh"], ws["qkv"][l], 3 * d, 0, e["nq1"], cos, sin, dqkv, 3 * d, 0, B, S, H, True,
                                 cfg.qk_norm_eps)
-            ops.qknorm_rope_bwd(ws["dkh"], ws["qkv"][l], 3 * d, d, e["nk1"], cos, sin, ws["dqkv"], 3 * d, d, B, S, H, True,
+            ops.qknorm_rope_bwd(ws["dkh"], ws["qkv"][l], 3 * d, d, e["nk1"], cos, sin, dqkv, 3 * d, d, B, S, H, True,
                                 cfg.qk_norm_eps)
-            ops.qknorm_rope_bwd(ws["dvh"], ws["qkv"][l], 3 * d, 2 * d, None, None, None, ws["dqkv"], 3 * d, 2 * d, B, S, H,
+            ops.qknorm_rope_bwd(ws["dvh"], ws["qkv"][l], 3 * d, 2 * d, None, None, None, dqkv, 3 * d, 2 * d, B, S, H,
                                 False, cfg.qk_norm_eps)
-            du = self._lora_bwd(ws["dqkv"], ws["n1"][l], ws["u_qkv"][l], ws["du_big"], e, "qkv", R, 3 * d, d, 3)
+            du = self._lora_du(dqkv, ws["du_qkv"][l], e, "qkv", R, 3 * d, 3)
             if l == 0 and self.skip_block0_dx:
                 break  # nothing trainable upstream of block 0's adapters (proj_in / embeds are frozen)
-            ops.gemm(ws["dqkv"], e["Wqkv"], ws["dn"], M=R, N=d, K=3 * d, b_mn=True, A2=du, B2=e["Ab_qkv"], K2=3 * rp)
+            ops.gemm(dqkv, e["Wqkv"], ws["dn"], M=R, N=d, K=3 * d, b_mn=True, A2=du, B2=e["Ab_qkv"], K2=3 * rp)
             # dh0 = dh1 + norm_bwd(dn1; h_in, scale_msa=row 1) ; g = dh0 * gate_mlp of block l-1
             prev = self._blk[l - 1]["sst"] if l > 0 else None
             ops.norm_modulate_bwd(ws["dn"], ws["h"][l], dh, dh, sst[1], temb[:, d:], 6 * d, R, d, S, cfg.norm_eps,
                                   gate2_tab=prev[5] if l > 0 else None, gate2_emb=temb[:, 5 * d:] if l > 0 else None,
                                   out2=g if l > 0 else None)
+        self._lora_wgrads_all(ws, R, RL)

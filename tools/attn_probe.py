@@ -1,0 +1,19 @@
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from finetrainers_b200 import ops
+dev="cuda"; torch.manual_seed(0)
+H,S,D=32,2688,2048
+rnd=lambda *s: torch.randn(*s,device=dev).bfloat16()
+q,k,v=rnd(1,H,S,64),rnd(1,H,S,64),rnd(1,H,S,64)
+ao=torch.empty(1,S,D,device=dev,dtype=torch.bfloat16); lse=torch.empty(1,H,S,device=dev)
+dout=rnd(1,S,D); dq,dk,dv=torch.empty_like(q),torch.empty_like(k),torch.empty_like(v)
+delta=torch.empty(ops.attn_bwd_ws_floats(1,H,S,S),device=dev)
+def t(fn,n=10):
+    for _ in range(3): fn()
+    e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1)/n*1e3
+print(os.environ.get("B2D_ATTN_DBG","0"), os.environ.get("B2D_ATTN_FWD","pp"), os.environ.get("B2D_ATTN_BWD","pp"),
+      "fwd %.1f us"%t(lambda: ops.attn_fwd(q,k,v,None,ao,lse,1,H,S,S,0.125)),
+      "bwd %.1f us"%t(lambda: ops.attn_bwd(q,k,v,None,ao,dout,lse,delta,dq,dk,dv,1,H,S,S,0.125)), flush=True)
