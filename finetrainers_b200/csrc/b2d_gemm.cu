@@ -194,16 +194,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                     const uint32_t sB = sA + A_STAGE_BYTES;
                     const bool ext = i >= n_main;
                     const bool a_mn = (A_MN != 0) && !ext;
+                    // descriptor low words advance by a constant per 16-element k-step (K-major: +32 B in the 128 B row;
+                    // MN-major: +16 rows of 128 B); the high word is a constant
+                    const uint32_t alo = a_mn ? sdesc_lo_mnmajor(sA) : sdesc_lo_kmajor(sA);
+                    const uint32_t blo = (B_MN != 0) ? sdesc_lo_mnmajor(sB) : sdesc_lo_kmajor(sB);
+                    const uint32_t astep = a_mn ? SDESC_KSTEP_MNMAJOR : SDESC_KSTEP_KMAJOR;
+                    constexpr uint32_t bstep = (B_MN != 0) ? SDESC_KSTEP_MNMAJOR : SDESC_KSTEP_KMAJOR;
+                    const uint32_t idesc = ext ? idesc_ext : idesc_main;
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k) {
-                        // K-major: +32 B per 16 K elements inside the 128 B swizzle row.
-                        // MN-major: +16 K-rows * 128 B.
-                        uint64_t ad = a_mn ? make_sdesc_sw128(sA + k * 2048, 8192, 1024)
-                                           : make_sdesc_sw128(sA + k * 32, 16, 1024);
-                        uint64_t bd = (B_MN != 0) ? make_sdesc_sw128(sB + k * 2048, 8192, 1024)
-                                                  : make_sdesc_sw128(sB + k * 32, 16, 1024);
-                        umma_f16(tmem_d, ad, bd, ext ? idesc_ext : idesc_main, (i > 0 || k > 0) ? 1u : 0u);
-                    }
+                    for (int k = 0; k < BLOCK_K / 16; ++k)
+                        umma_f16_lo(tmem_d, alo + k * astep, blo + k * bstep, idesc, (i > 0 || k > 0) ? 1u : 0u);
                     umma_commit(&empty_bar[stage]);
                     if (++stage == Cfg::STAGES) {
                         stage = 0;

@@ -42,21 +42,39 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    // with a suspend-time hint the waiting thread is parked by the hardware until the phase completes (or the hint
+    // expires) instead of re-issuing the probe every few cycles and stealing issue slots from the compute warps
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P;\n\t"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
+}
+
+// pure spin on test_wait (never parks the thread): lowest wake-up latency, burns issue slots
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
 }
 
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads of smem)
@@ -171,6 +189,28 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
+}
+
+// Cheap issue path for short MMAs (attention tiles, skinny GEMMs), where the single issuing thread is the bottleneck:
+// the descriptor's high word is a compile-time constant (SBO = 1024 B, version 1, SWIZZLE_128B) and the low word
+// (start address >> 4 | LBO >> 4 << 16) is advanced with one integer add per k-step.
+constexpr uint32_t SDESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t sdesc_lo_kmajor(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t sdesc_lo_mnmajor(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (512u << 16); }
+constexpr uint32_t SDESC_KSTEP_KMAJOR = 32 >> 4;     // +16 K elements inside a 128 B row
+constexpr uint32_t SDESC_KSTEP_MNMAJOR = 2048 >> 4;  // +16 K rows of 128 B
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(SDESC_HI_SW128)
+        : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
