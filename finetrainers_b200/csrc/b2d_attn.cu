@@ -345,31 +345,33 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
 }
 
 // ================================================================================================
-// forward, ping-pong version: ONE CTA per SM owns TWO 128-query tiles (one per softmax warpgroup); K/V tiles are loaded
-// once for both; the MMA warp alternates  S_t(j+1) / P_t V(j)  between the two tiles so that the tensor pipe works on one
-// tile while the other tile's warpgroup exponentiates.
+// forward, decoupled version: ONE CTA per SM, one 128-query tile, S DOUBLE-buffered in TMEM and P double-buffered in
+// smem.  The MMA warp issues S(j+2) as soon as the softmax warps have drained S(j), so S(j+1) is already waiting when
+// softmax(j) finishes: the softmax warps never sit in the  "P ready -> PV issue -> commit -> S ready"  round trip
+// (~1.5 us on B200) that bounds the two-CTA version; they only wait on MMAs issued two tiles earlier.
+//     MMA     :  S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ...
+//     softmax :  [0]        [1]          [2]  ...          (back to back)
 // ================================================================================================
-constexpr int FPP_STAGES = 3;
-constexpr int FPP_THREADS = 320;
-constexpr int FPP_SMEM = 2 * TILE_BYTES /*Q0,Q1*/ + FPP_STAGES * 2 * TILE_BYTES /*K,V*/ + 2 * 2 * TILE_BYTES /*P0,P1*/ + 1024 + 256;
+constexpr int FDB_STAGES = 4;
+constexpr int FDB_SMEM = TILE_BYTES /*Q*/ + FDB_STAGES * 2 * TILE_BYTES /*K,V*/ + 2 * 2 * TILE_BYTES /*P[2]*/ + 1024 + 256;
 
-__global__ void __launch_bounds__(FPP_THREADS, 1) attn_fwd_pp_kernel(const __grid_constant__ AttnFwdParams p) {
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_db_kernel(const __grid_constant__ AttnFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                     // [2] tiles
-    uint8_t* sKV = sQ + 2 * TILE_BYTES;                     // stage s: K at +s*32K, V at +16K
-    uint8_t* sPall = sKV + FPP_STAGES * 2 * TILE_BYTES;     // P_t at + t*32K (2 swizzled chunks each)
+    uint8_t* sQ = smem;
+    uint8_t* sKV = sQ + TILE_BYTES;                         // stage s: K at +s*32K, V at +16K
+    uint8_t* sPall = sKV + FDB_STAGES * 2 * TILE_BYTES;     // P[b] at + b*32K (2 swizzled chunks each)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPall + 2 * 2 * TILE_BYTES);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;    // [3]
-    uint64_t* kv_empty = bars + 4;   // [3]
-    uint64_t* s_full = bars + 7;     // [2]
-    uint64_t* p_full = bars + 9;     // [2]
-    uint64_t* pv_done = bars + 11;   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* kv_full = bars + 1;                  // [4]
+    uint64_t* kv_empty = kv_full + FDB_STAGES;     // [4]
+    uint64_t* s_full = kv_empty + FDB_STAGES;      // [2]
+    uint64_t* p_full = s_full + 2;                 // [2]
+    uint64_t* pv_done = p_full + 2;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * 2 * TILE;
+    const int q0 = blockIdx.x * TILE;
     const int bh = blockIdx.y;
     const int b = bh / p.H, h = bh % p.H;
     const int n_kv = (p.Sk + TILE - 1) / TILE;
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(FPP_THREADS, 1) attn_fwd_pp_kernel(const __gri
         tma_prefetch_desc(&p.tmK);
         tma_prefetch_desc(&p.tmV);
         mbar_init(q_full, 1);
-        for (int i = 0; i < FPP_STAGES; ++i) {
+        for (int i = 0; i < FDB_STAGES; ++i) {
             mbar_init(&kv_full[i], 1);
             mbar_init(&kv_empty[i], 1);
         }
@@ -397,13 +399,13 @@ __global__ void __launch_bounds__(FPP_THREADS, 1) attn_fwd_pp_kernel(const __gri
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;  // S_t at 128*t, O_t at 256 + 64*t
+    const uint32_t tmem = *tmem_slot;  // S[b] at 128*b, O at 256
+    const uint32_t tO = tmem + 256;
 
     if (warp == 0) {
         if (elect_one()) {
-            mbar_expect_tx(q_full, 2 * TILE_BYTES);
+            mbar_expect_tx(q_full, TILE_BYTES);
             tma_load_4d(sQ, &p.tmQ, q_full, 0, h, q0, b);
-            tma_load_4d(sQ + TILE_BYTES, &p.tmQ, q_full, 0, h, q0 + TILE, b);
             int stage = 0;
             uint32_t phase = 0;
             for (int j = 0; j < n_kv; ++j) {
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(FPP_THREADS, 1) attn_fwd_pp_kernel(const __gri
                 mbar_expect_tx(&kv_full[stage], 2 * TILE_BYTES);
                 tma_load_4d(sKV + stage * 2 * TILE_BYTES, &p.tmK, &kv_full[stage], 0, h, j * TILE, b);
                 tma_load_4d(sKV + stage * 2 * TILE_BYTES + TILE_BYTES, &p.tmV, &kv_full[stage], 0, h, j * TILE, b);
-                if (++stage == FPP_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == FDB_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -419,63 +421,53 @@ __global__ void __launch_bounds__(FPP_THREADS, 1) attn_fwd_pp_kernel(const __gri
             constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
             constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
             mbar_wait(q_full, 0);
-            auto issue_s = [&](int t, int j) {
-                const uint32_t aQ = smem_u32(sQ + t * TILE_BYTES);
-                const uint32_t aK = smem_u32(sKV + (j % FPP_STAGES) * 2 * TILE_BYTES);
-                const uint32_t lq = sdesc_lo_kmajor(aQ), lk = sdesc_lo_kmajor(aK);
+            const uint32_t lq = sdesc_lo_kmajor(smem_u32(sQ));
+            auto issue_s = [&](int j) {
+                const int st = j % FDB_STAGES;
+                mbar_wait(&kv_full[st], (uint32_t)((j / FDB_STAGES) & 1));
+                tc_fence_after();
+                const uint32_t lk = sdesc_lo_kmajor(smem_u32(sKV + st * 2 * TILE_BYTES));
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma_f16_lo(tmem + t * 128, lq + k * SDESC_KSTEP_KMAJOR, lk + k * SDESC_KSTEP_KMAJOR, idesc_s, k > 0);
-                umma_commit(&s_full[t]);
+                    umma_f16_lo(tmem + (j & 1) * 128, lq + k * SDESC_KSTEP_KMAJOR, lk + k * SDESC_KSTEP_KMAJOR, idesc_s, k > 0);
+                umma_commit(&s_full[j & 1]);
             };
-            mbar_wait(&kv_full[0], 0);
-            tc_fence_after();
-            issue_s(0, 0);
-            issue_s(1, 0);
+            issue_s(0);
+            if (n_kv > 1) issue_s(1);
             for (int j = 0; j < n_kv; ++j) {
-                const int st = j % FPP_STAGES;
-                const uint32_t aV = smem_u32(sKV + st * 2 * TILE_BYTES + TILE_BYTES);
-                if (j + 1 < n_kv) {
-                    mbar_wait(&kv_full[(j + 1) % FPP_STAGES], (uint32_t)(((j + 1) / FPP_STAGES) & 1));
-                    tc_fence_after();
-                }
-#pragma unroll 1
-                for (int t = 0; t < 2; ++t) {
-                    mbar_wait(&p_full[t], (uint32_t)(j & 1));
-                    tc_fence_after();
-                    const uint32_t aP = smem_u32(sPall + t * 2 * TILE_BYTES);
-                    const uint32_t lp = sdesc_lo_kmajor(aP), lv = sdesc_lo_mnmajor(aV);
+                const int st = j % FDB_STAGES;
+                mbar_wait(&p_full[j & 1], (uint32_t)((j >> 1) & 1));  // P(j) written, S[j&1] drained
+                tc_fence_after();
+                const uint32_t lp = sdesc_lo_kmajor(smem_u32(sPall + (j & 1) * 2 * TILE_BYTES));
+                const uint32_t lv = sdesc_lo_mnmajor(smem_u32(sKV + st * 2 * TILE_BYTES + TILE_BYTES));
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma_f16_lo(tmem + 256 + t * 64, lp + (k >> 2) * (TILE_BYTES >> 4) + (k & 3) * SDESC_KSTEP_KMAJOR,
-                                    lv + k * SDESC_KSTEP_MNMAJOR, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(&pv_done[t]);
-                    if (t == 1) umma_commit(&kv_empty[st]);
-                    if (j + 1 < n_kv) issue_s(t, j + 1);  // S_t(j+1): its warpgroup finished reading S_t(j) before p_full
-                }
+                for (int k = 0; k < 8; ++k)
+                    umma_f16_lo(tO, lp + (k >> 2) * (TILE_BYTES >> 4) + (k & 3) * SDESC_KSTEP_KMAJOR,
+                                lv + k * SDESC_KSTEP_MNMAJOR, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&kv_empty[st]);
+                umma_commit(&pv_done[j & 1]);
+                if (j + 2 < n_kv) issue_s(j + 2);
             }
         }
     } else {
-        const int t = (warp - 2) >> 2;  // which query tile / warpgroup
         const int qd = warp & 3;
         const int r = qd * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const uint32_t tS = tmem + t * 128, tO = tmem + 256 + t * 64;
-        uint8_t* sP = sPall + t * 2 * TILE_BYTES;
-        uint64_t* my_s_full = &s_full[t];
-        uint64_t* my_p_full = &p_full[t];
-        uint64_t* my_pv_done = &pv_done[t];
         float m_run = -INFINITY, l_run = 0.f;
         const float* kb = p.key_bias ? p.key_bias + (long long)b * p.Sk : nullptr;
         for (int j = 0; j < n_kv; ++j) {
-            mbar_wait(my_s_full, j & 1);
+            const uint32_t tS = tmem + (j & 1) * 128;
+            uint8_t* sP = sPall + (j & 1) * 2 * TILE_BYTES;
+            mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
             tc_fence_after();
+            if (j >= 2) {  // P[j&1] was last read by PV(j-2)
+                mbar_wait(&pv_done[j & 1], (uint32_t)(((j - 2) >> 1) & 1));
+                tc_fence_after();
+            }
             const int kv0 = j * TILE;
             const bool fast = (kb == nullptr) && (kv0 + TILE <= p.Sk);
             bool done = false;
             if (fast && j > 0) {
-                mbar_wait(my_pv_done, (j - 1) & 1);
-                tc_fence_after();
                 float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
                 const float nm = -m_run;
@@ -531,9 +523,10 @@ __global__ void __launch_bounds__(FPP_THREADS, 1) attn_fwd_pp_kernel(const __gri
                     m_use = mx;
                 } else {
                     const bool need = (mx - m_run) > 8.0f;
-                    mbar_wait(my_pv_done, (j - 1) & 1);
-                    tc_fence_after();
                     if (__any_sync(0xffffffffu, need)) {
+                        // O must be quiescent: P V(j-1) was issued after our p_full(j-1) arrival; wait for it to retire
+                        mbar_wait(&pv_done[(j - 1) & 1], (uint32_t)(((j - 1) >> 1) & 1));
+                        tc_fence_after();
                         if (need) m_use = mx;
                         const float alpha = fast_exp2(m_run - m_use);
                         l_run *= alpha;
@@ -578,11 +571,12 @@ __global__ void __launch_bounds__(FPP_THREADS, 1) attn_fwd_pp_kernel(const __gri
             }
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(my_p_full);
+            mbar_arrive(&p_full[j & 1]);
         }
-        mbar_wait(my_pv_done, (n_kv - 1) & 1);
+        // all P V must have retired: the last two commits cover both pv_done barriers
+        mbar_wait(&pv_done[(n_kv - 1) & 1], (uint32_t)(((n_kv - 1) >> 1) & 1));
         tc_fence_after();
-        const int qrow = q0 + t * TILE + r;
+        const int qrow = q0 + r;
         const float inv_l = 1.f / l_run;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
@@ -1273,16 +1267,17 @@ extern "C" int b2d_attn_fwd(const void* q, const void* k, const void* v, const f
     p.lse = lse;
     p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
     p.scale_log2 = scale * LOG2E;
-    static const bool use_pp = []() { const char* e = getenv("B2D_ATTN_FWD"); return !(e && e[0] == 'c'); }();
+    // two kernels: "classic" (default; two CTAs per SM interleave MMA and softmax: 125 us at S=2688, H=32) and "db"
+    // (B2D_ATTN_FWD=db; one CTA per SM, S/P double-buffered so softmax never waits on the MMA round trip: 145 us today,
+    // its four softmax warps are latency-bound on their own -- kept as the base for an 8-warp version)
+    static const bool use_db = []() { const char* e = getenv("B2D_ATTN_FWD"); return e && e[0] == 'd'; }();
     if ((rc = set_smem((const void*)attn_fwd_kernel, FWD_SMEM, "attn_fwd"))) return rc;
-    if ((rc = set_smem((const void*)attn_fwd_pp_kernel, FPP_SMEM, "attn_fwd_pp"))) return rc;
-    if (use_pp && Sq > TILE) {
-        dim3 grid((Sq + 2 * TILE - 1) / (2 * TILE), B * H);
-        attn_fwd_pp_kernel<<<grid, FPP_THREADS, FPP_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-    } else {
-        dim3 grid((Sq + TILE - 1) / TILE, B * H);
+    if ((rc = set_smem((const void*)attn_fwd_db_kernel, FDB_SMEM, "attn_fwd_db"))) return rc;
+    dim3 grid((Sq + TILE - 1) / TILE, B * H);
+    if (use_db && Sk > 2 * TILE)
+        attn_fwd_db_kernel<<<grid, ATT_THREADS, FDB_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    else
         attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-    }
     B2D_CHECK_LAUNCH("attn_fwd");
     return 0;
 }
