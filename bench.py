@@ -134,6 +134,7 @@ def run_b200(args):
     from finetrainers_b200.trainer import SFTTrainStep
     from finetrainers_b200.parallel import B200ParallelBackend
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")

@@ -46,9 +46,11 @@ struct GemmKParams {
     int m_tiles, n_tiles, kb_main, kb_ext, total_work;
 };
 
-template <int BN>
+template <int BN, int B_MN>
 struct GemmCfg {
-    static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+    // K-major B: one [BN x 64] box.  MN-major B: ceil(BN/64) boxes of [64 k-rows x 64 n] (BN = 160 loads 192 columns
+    // and multiplies the first 160: the last 64-wide atom is used half).
+    static constexpr int B_STAGE_BYTES = B_MN ? ((BN + 63) / 64) * 8192 : BN * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = (220 * 1024 / STAGE_BYTES) > 8 ? 8 : (220 * 1024 / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -66,7 +68,7 @@ __device__ __forceinline__ uint4 ld_global_16B(const void* p) {
 
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmKParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, B_MN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                             tma_load_2d(sB, &p.tmB, &full_bar[stage], k0 + z * p.b_bcol, n0 + z * p.b_brow);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < BN / 64; ++j)
+                            for (int j = 0; j < (BN + 63) / 64; ++j)
                                 tma_load_2d(sB + j * 8192, &p.tmB, &full_bar[stage], n0 + 64 * j + z * p.b_bcol,
                                             k0 + z * p.b_brow);
                         }
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                             tma_load_2d(sB, &p.tmB2, &full_bar[stage], k2, n0);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < BN / 64; ++j)
+                            for (int j = 0; j < (BN + 63) / 64; ++j)
                                 tma_load_2d(sB + j * 8192, &p.tmB2, &full_bar[stage], n0 + 64 * j, k2);
                         }
                     }
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------
 template <int BN, int A_MN, int B_MN>
 static int launch_gemm(const GemmKParams& kp, int grid, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, B_MN>;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -426,8 +428,8 @@ static int launch_gemm(const GemmKParams& kp, int grid, cudaStream_t stream) {
 
 template <int BN>
 static int dispatch_major(const GemmKParams& kp, int a_mn, int b_mn, int grid, cudaStream_t s) {
-    if constexpr (BN % 64 != 0) {
-        if (a_mn) return launch_gemm<BN, 1, 0>(kp, grid, s);
+    if constexpr (BN % 64 != 0) {  // 160: K-major A only
+        if (b_mn) return launch_gemm<BN, 0, 1>(kp, grid, s);
         return launch_gemm<BN, 0, 0>(kp, grid, s);
     }
     if (!a_mn && !b_mn) return launch_gemm<BN, 0, 0>(kp, grid, s);
@@ -436,7 +438,7 @@ static int dispatch_major(const GemmKParams& kp, int a_mn, int b_mn, int grid, c
     return launch_gemm<BN, 1, 0>(kp, grid, s);
 }
 
-static int pick_block_n(int M, int N, int nsm, int work_mult, int b_mn, int group_n) {
+static int pick_block_n(int M, int N, int nsm, int work_mult, int a_mn, int b_mn, int group_n) {
     // minimise (waves * tile cost) over the candidate tile widths; cost ~ BN + fixed overhead.
     // 160 exists to beat wave quantisation at N = 2048 (13 x 21 = 273 tiles on 2 x 148 slots); MN-major B tiles are
     // built from 64-column TMA boxes, so they need BN % 64 == 0.
@@ -446,7 +448,7 @@ static int pick_block_n(int M, int N, int nsm, int work_mult, int b_mn, int grou
     int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
     for (int i = 0; i < 5; ++i) {
         int bn = cands[i];
-        if (b_mn && (bn % 64) != 0) continue;
+        if (a_mn && (bn % 64) != 0) continue;
         if (group_n > 0 && (group_n % bn) != 0) continue;
         if (bn > N && bn != 64) continue;
         int n_tiles = (N + bn - 1) / bn;
@@ -492,9 +494,9 @@ extern "C" int b2d_gemm(const b2d_gemm_desc* d, void* stream_v) {
     int nsm = device_sm_count();
     if (nsm <= 0) return B2D_ERR_CUDA;
     int max_ctas = d->max_ctas > 0 ? d->max_ctas : nsm;
-    int bn = d->block_n > 0 ? d->block_n : pick_block_n(d->M, d->N, max_ctas, splits * batch, d->b_mn_major, d->a2_group_n);
+    int bn = d->block_n > 0 ? d->block_n : pick_block_n(d->M, d->N, max_ctas, splits * batch, d->a_mn_major, d->b_mn_major, d->a2_group_n);
     if (bn != 64 && bn != 128 && bn != 160 && bn != 192 && bn != 256) return set_error(B2D_ERR_ARG, "gemm: bad block_n %d", bn);
-    if (d->b_mn_major && (bn % 64)) return set_error(B2D_ERR_ARG, "gemm: MN-major B needs block_n %% 64 == 0");
+    if ((bn % 64) && d->a_mn_major) return set_error(B2D_ERR_ARG, "gemm: block_n 160 needs a K-major A operand");
     if (d->a2_group_n > 0 && (d->a2_group_n % bn) != 0)
         return set_error(B2D_ERR_ARG, "gemm: a2_group_n (%d) must be a multiple of block_n (%d)", d->a2_group_n, bn);
 

@@ -60,7 +60,7 @@ def check_gemm():
         A = rnd(M, K)
         Bt = rnd(K, N, scale=0.05)
         ref = A.float() @ Bt.float()
-        for bn in (64, 128, 256):
+        for bn in (64, 128, 160, 256):
             out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
             ops.gemm(A, Bt, out, M=M, N=N, K=K, b_mn=True, block_n=bn)
             report(f"gemm K/MN M{M} N{N} K{K} bn{bn}", out, ref, 1e-2)
