@@ -67,8 +67,11 @@ def load():
         if _lib is not None:
             return _lib
         if not os.path.exists(LIB_PATH):
-            raise B2DError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                           "(there is no CPU or PyTorch fallback for the b200 hot path)")
+            try:  # source-only checkout: compile once with nvcc (no other implementation exists to fall back to)
+                build()
+            except Exception as e:  # noqa: BLE001
+                raise B2DError(f"{LIB_PATH} not found and building it failed ({e}); there is no CPU or PyTorch "
+                               "fallback for the b200 hot path") from e
         lib = C.CDLL(LIB_PATH)
         lib.b2d_last_error.restype = C.c_char_p
         lib.b2d_version.restype = C.c_int

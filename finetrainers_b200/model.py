@@ -224,6 +224,28 @@ class B200LTXTransformer(nn.Module):
     def lora_parameters(self) -> List[nn.Parameter]:
         return [p for n, p in self.named_parameters() if "lora_" in n]
 
+    def lora_state_dict(self) -> Dict[str, torch.Tensor]:
+        """What ``peft.get_peft_model_state_dict`` returns for the adapters (adapter name stripped), contiguous CPU
+        tensors — the ``transformer_state_dict`` finetrainers hands to ``LTXPipeline.save_lora_weights``
+        (``base_specification.py:379-397``, ``trainer.py:279-306``)."""
+        return {n.replace(".default.weight", ".weight"): p.detach().to("cpu").contiguous().clone()
+                for n, p in self.named_parameters() if "lora_" in n}
+
+    def save_lora_weights(self, directory: str, metadata: Optional[Dict[str, str]] = None) -> str:
+        """Writes ``pytorch_lora_weights.safetensors`` with diffusers' ``transformer.`` key prefix (loadable with
+        ``pipe.load_lora_weights``), plus the LoRA config as metadata like the reference's save hook."""
+        import json
+        import os
+        from safetensors.torch import save_file
+        os.makedirs(directory, exist_ok=True)
+        sd = {"transformer." + k: v for k, v in self.lora_state_dict().items()}
+        meta = {"format": "pt", "lora_config": json.dumps({"r": self.lora_rank, "lora_alpha": self.lora_rank * self.lora_scaling,
+                                                           "target_modules": list(LORA_TARGETS)})}
+        meta.update(metadata or {})
+        path = os.path.join(directory, "pytorch_lora_weights.safetensors")
+        save_file(sd, path, metadata=meta)
+        return path
+
     @torch.no_grad()
     def prepare(self):
         """Pack weights into the fused layouts the kernels consume and re-point the parameters into them."""

@@ -123,3 +123,42 @@ def test_full_size_forward_loss_matches_oracle():
                                        backward=False)
     assert abs(loss_b - loss_o.item()) / abs(loss_o.item()) < 1e-3
     assert rel_err(pred_b, pred_o) < 5e-2
+
+
+def test_cuda_graph_step_matches_eager_and_grad_accumulation():
+    """The captured step (one CUDA graph replay per micro-step) reproduces the eager step; two accumulated micro-steps
+    equal one step on the concatenated batch statistics (loss averaged, gradients summed/scaled: trainer.py:479-480)."""
+    from finetrainers_b200.trainer import SFTTrainStep
+    from oracle import ltx_oracle as O
+    losses, params = {}, {}
+    for mode in ("eager", "graph"):
+        _, om, bm = build_pair(SMALL, 64, seed=1)
+        st = SFTTrainStep(bm, flow_weighting_scheme="none", use_cuda_graph=(mode == "graph"), seed=5)
+        st.spec.first_frame_conditioning_p = 0.0
+        ls = []
+        for i in range(5):  # graph mode: 2 eager warm-ups, capture on the 3rd call, replays after
+            batch = O.make_synthetic_batch(om.cfg, 2, 2, 4, 8, text_len=16, seed=100 + i)
+            cond = {"encoder_hidden_states": batch["encoder_hidden_states"].cuda(), "encoder_attention_mask": batch["encoder_attention_mask"].cuda()}
+            lat = {"latents": batch["latents"].cuda(), "latents_mean": batch["latents_mean"].cuda(), "latents_std": batch["latents_std"].cuda()}
+            m = st.train_step(cond, lat, sigmas=batch["sigmas"].view(-1).cuda(), noise=batch["noise"].cuda(), sync_metrics=True)
+            ls.append(m["train/global_avg_loss"])
+        losses[mode] = ls
+        params[mode] = bm.lora_flat.clone()
+    for a, b in zip(losses["eager"], losses["graph"]):
+        assert abs(a - b) / abs(a) < 1e-4, (losses["eager"], losses["graph"])
+    assert (params["eager"] - params["graph"]).abs().max().item() < 1e-5
+    # gradient accumulation: 2 micro-steps with accum=2 leave grad = mean of the two micro-gradients
+    _, om, bm = build_pair(SMALL, 64, seed=1)
+    st = SFTTrainStep(bm, flow_weighting_scheme="none", gradient_accumulation_steps=2)
+    st.spec.first_frame_conditioning_p = 0.0
+    gs = []
+    for i in range(2):
+        batch = O.make_synthetic_batch(om.cfg, 1, 2, 4, 8, text_len=16, seed=200 + i)
+        cond = {"encoder_hidden_states": batch["encoder_hidden_states"].cuda(), "encoder_attention_mask": batch["encoder_attention_mask"].cuda()}
+        lat = {"latents": batch["latents"].cuda(), "latents_mean": batch["latents_mean"].cuda(), "latents_std": batch["latents_std"].cuda()}
+        before = bm.lora_grad_flat.clone()
+        st.micro_step(cond, lat, sigmas=batch["sigmas"].view(-1).cuda(), noise=batch["noise"].cuda())
+        gs.append(bm.lora_grad_flat - before)
+    torch.cuda.synchronize()
+    assert st.micro == 2 and gs[0].abs().max() > 0 and gs[1].abs().max() > 0
+    assert torch.allclose(bm.lora_grad_flat, gs[0] + gs[1], rtol=1e-4, atol=1e-9)

@@ -137,3 +137,38 @@ def test_parallel_backend_world2_gloo(tmp_path):
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("WORKER_OK") == 2
+
+
+def test_precomputed_reader_follows_reference_layout(tmp_path):
+    """{data_type}-{index}.pt items, rank r owns indices r*num_items + i (precomputation.py:334-341)."""
+    from finetrainers_b200.data import PrecomputedReader, save_item
+    for i in range(4):
+        save_item({"latents": torch.full((1, 8, 1, 2, 2), float(i)), "num_frames": 1}, i, tmp_path, "latent")
+    rd = PrecomputedReader(tmp_path, "latent", rank=0, world_size=1, device=None)
+    assert len(rd) == 4
+    vals = [int(it["latents"][0, 0, 0, 0, 0]) for it in rd]
+    assert vals == [0, 1, 2, 3] and rd.requires_data
+
+
+def test_lora_export_keys_and_values(tmp_path):
+    """adapters export under diffusers/peft names and round-trip bit-exactly."""
+    from safetensors.torch import load_file
+    from finetrainers_b200.model import B200LTXTransformer, LTXConfig
+    cfg = LTXConfig(in_channels=32, out_channels=32, num_attention_heads=2, attention_head_dim=64, cross_attention_dim=128,
+                    num_layers=1, caption_channels=64)
+    m = B200LTXTransformer(cfg, torch.bfloat16, "cpu")
+    with torch.no_grad():
+        for p in m.parameters():
+            p.normal_(0, 0.02)
+    m.add_adapter(16, 16)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "lora_B" in n:
+                p.normal_(0, 0.01)
+    m.prepare()
+    path = m.save_lora_weights(tmp_path)
+    sd = load_file(path)
+    k = "transformer.transformer_blocks.0.attn2.to_out.0.lora_B.weight"
+    assert k in sd and sd[k].shape == (128, 16) and sd[k].dtype == torch.float32
+    assert torch.equal(sd[k], m.transformer_blocks[0].attn2.to_out[0].lora_B["default"].weight.detach())
+    assert len(sd) == 16
