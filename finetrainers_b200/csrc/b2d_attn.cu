@@ -44,6 +44,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 // ================================================================================================
 struct AttnFwdParams {
     CUtensorMap tmQ, tmK, tmV;
+    CUtensorMap tmK64, tmV64;  // same tensors, 64-row boxes (decoupled kernel)
     const float* key_bias;  // [B, Sk] or null
     __nv_bfloat16* out;     // [B, Sq, H*64]
     float* lse;             // [B, H, Sq]
@@ -345,23 +346,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
 }
 
 // ================================================================================================
-// forward, decoupled version: ONE CTA per SM, one 128-query tile, S DOUBLE-buffered in TMEM and P double-buffered in
-// smem.  The MMA warp issues S(j+2) as soon as the softmax warps have drained S(j), so S(j+1) is already waiting when
-// softmax(j) finishes: the softmax warps never sit in the  "P ready -> PV issue -> commit -> S ready"  round trip
-// (~1.5 us on B200) that bounds the two-CTA version; they only wait on MMAs issued two tiles earlier.
+// forward, decoupled version: 64-wide key tiles, S DOUBLE-buffered in TMEM (2 x 64 columns + 64 for O = 192 -> 256
+// allocated) and P double-buffered in smem, TWO CTAs per SM.  The MMA warp issues S(j+2) as soon as the softmax warps
+// have drained S(j), so S(j+1) is already waiting when softmax(j) finishes: the softmax warps never sit in the
+// "P ready -> PV issue -> commit -> S ready" round trip (~1.5 us on B200); they only wait on MMAs issued two tiles earlier.
 //     MMA     :  S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ...
 //     softmax :  [0]        [1]          [2]  ...          (back to back)
 // ================================================================================================
+constexpr int FDB_KV = 64;                                  // key rows per tile
 constexpr int FDB_STAGES = 4;
-constexpr int FDB_SMEM = TILE_BYTES /*Q*/ + FDB_STAGES * 2 * TILE_BYTES /*K,V*/ + 2 * 2 * TILE_BYTES /*P[2]*/ + 1024 + 256;
+constexpr int FDB_KV_BYTES = FDB_KV * HD * 2;               // 8 KB (K or V tile)
+constexpr int FDB_P_BYTES = TILE * FDB_KV * 2;              // 16 KB (one swizzled chunk)
+constexpr int FDB_SMEM = TILE_BYTES /*Q*/ + FDB_STAGES * 2 * FDB_KV_BYTES + 2 * FDB_P_BYTES + 256;  // 112.25 KB
 
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_db_kernel(const __grid_constant__ AttnFwdParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __grid_constant__ AttnFwdParams p) {
+    extern __shared__ uint8_t smem_fdb[];  // no static smem: the dynamic window starts 1024-aligned
+    uint8_t* smem = smem_fdb;
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* sQ = smem;
-    uint8_t* sKV = sQ + TILE_BYTES;                         // stage s: K at +s*32K, V at +16K
-    uint8_t* sPall = sKV + FDB_STAGES * 2 * TILE_BYTES;     // P[b] at + b*32K (2 swizzled chunks each)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sPall + 2 * 2 * TILE_BYTES);
+    uint8_t* sKV = sQ + TILE_BYTES;                         // stage s: K at +s*16K, V at +8K
+    uint8_t* sPall = sKV + FDB_STAGES * 2 * FDB_KV_BYTES;   // P[b] at + b*16K
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sPall + 2 * FDB_P_BYTES);
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;                  // [4]
     uint64_t* kv_empty = kv_full + FDB_STAGES;     // [4]
@@ -374,7 +379,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_db_kernel(const __gri
     const int q0 = blockIdx.x * TILE;
     const int bh = blockIdx.y;
     const int b = bh / p.H, h = bh % p.H;
-    const int n_kv = (p.Sk + TILE - 1) / TILE;
+    const int n_kv = (p.Sk + FDB_KV - 1) / FDB_KV;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmQ);
@@ -393,14 +398,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_db_kernel(const __gri
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, 256);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;  // S[b] at 128*b, O at 256
-    const uint32_t tO = tmem + 256;
+    const uint32_t tmem = *tmem_slot;  // S[b] at 64*b, O at 128
+    const uint32_t tO = tmem + 128;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -410,15 +415,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_db_kernel(const __gri
             uint32_t phase = 0;
             for (int j = 0; j < n_kv; ++j) {
                 mbar_wait(&kv_empty[stage], phase ^ 1);
-                mbar_expect_tx(&kv_full[stage], 2 * TILE_BYTES);
-                tma_load_4d(sKV + stage * 2 * TILE_BYTES, &p.tmK, &kv_full[stage], 0, h, j * TILE, b);
-                tma_load_4d(sKV + stage * 2 * TILE_BYTES + TILE_BYTES, &p.tmV, &kv_full[stage], 0, h, j * TILE, b);
+                mbar_expect_tx(&kv_full[stage], 2 * FDB_KV_BYTES);
+                tma_load_4d(sKV + stage * 2 * FDB_KV_BYTES, &p.tmK64, &kv_full[stage], 0, h, j * FDB_KV, b);
+                tma_load_4d(sKV + stage * 2 * FDB_KV_BYTES + FDB_KV_BYTES, &p.tmV64, &kv_full[stage], 0, h, j * FDB_KV, b);
                 if (++stage == FDB_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, FDB_KV, 0, 0);
             constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
             mbar_wait(q_full, 0);
             const uint32_t lq = sdesc_lo_kmajor(smem_u32(sQ));
@@ -426,10 +431,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_db_kernel(const __gri
                 const int st = j % FDB_STAGES;
                 mbar_wait(&kv_full[st], (uint32_t)((j / FDB_STAGES) & 1));
                 tc_fence_after();
-                const uint32_t lk = sdesc_lo_kmajor(smem_u32(sKV + st * 2 * TILE_BYTES));
+                const uint32_t lk = sdesc_lo_kmajor(smem_u32(sKV + st * 2 * FDB_KV_BYTES));
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma_f16_lo(tmem + (j & 1) * 128, lq + k * SDESC_KSTEP_KMAJOR, lk + k * SDESC_KSTEP_KMAJOR, idesc_s, k > 0);
+                    umma_f16_lo(tmem + (j & 1) * 64, lq + k * SDESC_KSTEP_KMAJOR, lk + k * SDESC_KSTEP_KMAJOR, idesc_s, k > 0);
                 umma_commit(&s_full[j & 1]);
             };
             issue_s(0);
@@ -438,12 +443,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_db_kernel(const __gri
                 const int st = j % FDB_STAGES;
                 mbar_wait(&p_full[j & 1], (uint32_t)((j >> 1) & 1));  // P(j) written, S[j&1] drained
                 tc_fence_after();
-                const uint32_t lp = sdesc_lo_kmajor(smem_u32(sPall + (j & 1) * 2 * TILE_BYTES));
-                const uint32_t lv = sdesc_lo_mnmajor(smem_u32(sKV + st * 2 * TILE_BYTES + TILE_BYTES));
+                const uint32_t lp = sdesc_lo_kmajor(smem_u32(sPall + (j & 1) * FDB_P_BYTES));
+                const uint32_t lv = sdesc_lo_mnmajor(smem_u32(sKV + st * 2 * FDB_KV_BYTES + FDB_KV_BYTES));
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    umma_f16_lo(tO, lp + (k >> 2) * (TILE_BYTES >> 4) + (k & 3) * SDESC_KSTEP_KMAJOR,
-                                lv + k * SDESC_KSTEP_MNMAJOR, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < FDB_KV / 16; ++k)
+                    umma_f16_lo(tO, lp + k * SDESC_KSTEP_KMAJOR, lv + k * SDESC_KSTEP_MNMAJOR, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&kv_empty[st]);
                 umma_commit(&pv_done[j & 1]);
                 if (j + 2 < n_kv) issue_s(j + 2);
@@ -456,23 +460,23 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_db_kernel(const __gri
         float m_run = -INFINITY, l_run = 0.f;
         const float* kb = p.key_bias ? p.key_bias + (long long)b * p.Sk : nullptr;
         for (int j = 0; j < n_kv; ++j) {
-            const uint32_t tS = tmem + (j & 1) * 128;
-            uint8_t* sP = sPall + (j & 1) * 2 * TILE_BYTES;
+            const uint32_t tS = tmem + (j & 1) * 64;
+            uint8_t* sP = sPall + (j & 1) * FDB_P_BYTES;
             mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
             tc_fence_after();
             if (j >= 2) {  // P[j&1] was last read by PV(j-2)
                 mbar_wait(&pv_done[j & 1], (uint32_t)(((j - 2) >> 1) & 1));
                 tc_fence_after();
             }
-            const int kv0 = j * TILE;
-            const bool fast = (kb == nullptr) && (kv0 + TILE <= p.Sk);
+            const int kv0 = j * FDB_KV;
+            const bool fast = (kb == nullptr) && (kv0 + FDB_KV <= p.Sk);
             bool done = false;
             if (fast && j > 0) {
                 float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
                 const float nm = -m_run;
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < FDB_KV / 32; ++c) {
                     uint32_t v[32];
                     tmem_ld32(tS + lane_off + c * 32, v);
                     tmem_ld_wait();
@@ -488,12 +492,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_db_kernel(const __gri
                         pv[e + 3] = fast_exp2(fmaf(a3, p.scale_log2, nm));
                         l0 += pv[e]; l1 += pv[e + 1]; l2 += pv[e + 2]; l3 += pv[e + 3];
                     }
-                    uint8_t* chunk = sP + (c >> 1) * TILE_BYTES;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         uint4 w = make_uint4(pack_bf16x2(pv[u * 8], pv[u * 8 + 1]), pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]),
                                              pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]), pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]));
-                        *reinterpret_cast<uint4*>(chunk + sw128_off(r, (c & 1) * 4 + u)) = w;
+                        *reinterpret_cast<uint4*>(sP + sw128_off(r, c * 4 + u)) = w;
                     }
                 }
                 const float mxo = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) * p.scale_log2;
@@ -505,7 +508,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_db_kernel(const __gri
             if (!done) {
                 float mx = -INFINITY;
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < FDB_KV / 32; ++c) {
                     uint32_t v[32];
                     tmem_ld32(tS + lane_off + c * 32, v);
                     tmem_ld_wait();
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_db_kernel(const __gri
                 m_run = m_use;
                 float l0 = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < FDB_KV / 32; ++c) {
                     uint32_t v[32];
                     tmem_ld32(tS + lane_off + c * 32, v);
                     tmem_ld_wait();
@@ -559,12 +562,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_db_kernel(const __gri
                         pv[e] = pe;
                         l0 += pe;
                     }
-                    uint8_t* chunk = sP + (c >> 1) * TILE_BYTES;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         uint4 w = make_uint4(pack_bf16x2(pv[u * 8], pv[u * 8 + 1]), pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]),
                                              pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]), pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]));
-                        *reinterpret_cast<uint4*>(chunk + sw128_off(r, (c & 1) * 4 + u)) = w;
+                        *reinterpret_cast<uint4*>(sP + sw128_off(r, c * 4 + u)) = w;
                     }
                 }
                 l_run += l0;
@@ -573,7 +575,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_db_kernel(const __gri
             tc_fence_before();
             mbar_arrive(&p_full[j & 1]);
         }
-        // all P V must have retired: the last two commits cover both pv_done barriers
+        // all P V must have retired: commits retire in order, so the last tile's barrier covers every earlier one
         mbar_wait(&pv_done[(n_kv - 1) & 1], (uint32_t)(((n_kv - 1) >> 1) & 1));
         tc_fence_after();
         const int qrow = q0 + r;
@@ -602,7 +604,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_db_kernel(const __gri
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem, 512);
+        tmem_dealloc(tmem, 256);
     }
 }
 
@@ -1262,19 +1264,21 @@ extern "C" int b2d_attn_fwd(const void* q, const void* k, const void* v, const f
     if ((rc = make_head_map(&p.tmQ, q, B, H, Sq, (long long)Sq * 64, 64, (long long)H * Sq * 64))) return rc;
     if ((rc = make_head_map(&p.tmK, k, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64))) return rc;
     if ((rc = make_head_map(&p.tmV, v, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64))) return rc;
+    if ((rc = make_head_map(&p.tmK64, k, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64, FDB_KV))) return rc;
+    if ((rc = make_head_map(&p.tmV64, v, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64, FDB_KV))) return rc;
     p.key_bias = key_bias;
     p.out = (__nv_bfloat16*)out;
     p.lse = lse;
     p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
     p.scale_log2 = scale * LOG2E;
-    // two kernels: "classic" (default; two CTAs per SM interleave MMA and softmax: 125 us at S=2688, H=32) and "db"
-    // (B2D_ATTN_FWD=db; one CTA per SM, S/P double-buffered so softmax never waits on the MMA round trip: 145 us today,
-    // its four softmax warps are latency-bound on their own -- kept as the base for an 8-warp version)
-    static const bool use_db = []() { const char* e = getenv("B2D_ATTN_FWD"); return e && e[0] == 'd'; }();
+    // two kernels: "db" (default for long key sequences: 64-wide key tiles, S/P double-buffered so softmax never waits on
+    // the MMA round trip, 2 CTAs/SM; 120 us at S=2688, H=32, at which point the MUFU ex2 unit is ~85 % busy) and "classic"
+    // (B2D_ATTN_FWD=classic; 128-wide tiles, 2 CTAs/SM interleaving MMA and softmax, 125 us; used when Sk <= 128)
+    static const bool force_classic = []() { const char* e = getenv("B2D_ATTN_FWD"); return e && e[0] == 'c'; }();
     if ((rc = set_smem((const void*)attn_fwd_kernel, FWD_SMEM, "attn_fwd"))) return rc;
     if ((rc = set_smem((const void*)attn_fwd_db_kernel, FDB_SMEM, "attn_fwd_db"))) return rc;
     dim3 grid((Sq + TILE - 1) / TILE, B * H);
-    if (use_db && Sk > 2 * TILE)
+    if (!force_classic && Sk > TILE)
         attn_fwd_db_kernel<<<grid, ATT_THREADS, FDB_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     else
         attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
