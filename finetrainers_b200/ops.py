@@ -175,7 +175,9 @@ def attn_bwd(q, k, v, key_bias, out, dout, lse, delta_ws, dq, dk, dv, B, H, Sq, 
         check(_l.load().b2d_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(key_bias), _ptr(out), _ptr(dout), _ptr(lse),
                                      _ptr(delta_ws), _ptr(dq), _ptr(dk), _ptr(dv), B, H, Sq, Sk, C.c_float(scale),
                                      _stream()), "attn_bwd")
-    _count(3 if Sk > 512 else 6)
+    # kernels launched: delta + dK/dV + dQ, plus two fp32->bf16 converts when the cross-attention split path runs
+    split = (B * H * ((Sk + 127) // 128) < 96) and Sk <= 512 and ((Sq + 63) // 64) >= 8
+    _count(5 if split else 3)
 
 
 def prep_noise_pack(latents, noise, mean, std, sigma, sigma_ff, x_t, target, B, Cc, F, HW):
