@@ -943,7 +943,7 @@ constexpr int PP_NBUF = 3;                            // S/dP TMEM buffers
 constexpr int PP_THREADS = 320;                       // TMA warp, MMA warp, 2 x 4 consumer warps
 constexpr int PP_Y_BYTES = PP_TY * HD * 2;            // 8 KB
 constexpr int PP_PS_BYTES = TILE * PP_TY * 2;         // 16 KB
-constexpr int PP_SMEM = 2 * TILE_BYTES + PP_STAGES * 2 * PP_Y_BYTES + 4 * PP_PS_BYTES + PP_STAGES * 2 * PP_TY * 4 + 1024 + 256;
+constexpr int PP_SMEM = 2 * TILE_BYTES + PP_STAGES * 2 * PP_Y_BYTES + 2 * PP_NBUF * PP_PS_BYTES + PP_STAGES * 2 * PP_TY * 4 + 1024 + 256;
 
 template <bool DKV>
 __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid_constant__ AttnBwdParams p) {
@@ -953,18 +953,18 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
     uint8_t* sX1 = smem;
     uint8_t* sX2 = sX1 + TILE_BYTES;
     uint8_t* sY = sX2 + TILE_BYTES;                         // stage s: Y1 at +s*2*Y_BYTES, Y2 right after
-    uint8_t* sP = sY + PP_STAGES * 2 * PP_Y_BYTES;          // P^T buffers [2] (one per warpgroup)
-    uint8_t* sDS = sP + 2 * PP_PS_BYTES;                    // dS buffers [2]
-    float* sColA = reinterpret_cast<float*>(sDS + 2 * PP_PS_BYTES);  // [stages][TY]
+    uint8_t* sP = sY + PP_STAGES * 2 * PP_Y_BYTES;          // P^T buffers [3] (one per accumulator buffer)
+    uint8_t* sDS = sP + PP_NBUF * PP_PS_BYTES;              // dS buffers [3]
+    float* sColA = reinterpret_cast<float*>(sDS + PP_NBUF * PP_PS_BYTES);  // [stages][TY]
     float* sColD = sColA + PP_STAGES * TY;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sColD + PP_STAGES * TY);
     uint64_t* x_full = bars;
     uint64_t* y_full = bars + 1;                   // [PP_STAGES]
     uint64_t* y_empty = y_full + PP_STAGES;        // [PP_STAGES]
     uint64_t* s_full = y_empty + PP_STAGES;        // [PP_NBUF]
-    uint64_t* ds_full = s_full + PP_NBUF;          // [2]
-    uint64_t* mm_done = ds_full + 2;               // [2]
-    uint64_t* all_done = mm_done + 2;
+    uint64_t* ds_full = s_full + PP_NBUF;          // [2]  (per warpgroup)
+    uint64_t* mm_done = ds_full + 2;               // [PP_NBUF] (per P/dS buffer)
+    uint64_t* all_done = mm_done + PP_NBUF;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -988,11 +988,11 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             mbar_init(&y_full[i], 1);
             mbar_init(&y_empty[i], 1);
         }
-        for (int i = 0; i < PP_NBUF; ++i) mbar_init(&s_full[i], 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&ds_full[i], 128);
+        for (int i = 0; i < PP_NBUF; ++i) {
+            mbar_init(&s_full[i], 1);
             mbar_init(&mm_done[i], 1);
         }
+        for (int i = 0; i < 2; ++i) mbar_init(&ds_full[i], 128);
         mbar_init(all_done, 1);
         fence_mbar_init();
     }
@@ -1057,7 +1057,11 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
                 mbar_wait(&ds_full[bsel], (uint32_t)((it >> 1) & 1));  // consumer finished tile it: P/dS ready, S/dP[it%3] free
                 tc_fence_after();
                 const uint32_t aY1 = smem_u32(sY + st * 2 * PP_Y_BYTES), aY2 = aY1 + PP_Y_BYTES;
-                const uint32_t aP = smem_u32(sP + bsel * PP_PS_BYTES), aDS = smem_u32(sDS + bsel * PP_PS_BYTES);
+                const int kbuf = it % PP_NBUF;
+                const uint32_t aP = smem_u32(sP + kbuf * PP_PS_BYTES), aDS = smem_u32(sDS + kbuf * PP_PS_BYTES);
+                // refill the drained accumulator buffer first: S/dP(it+3) heads the consumers' chain, dV/dK(it) does not
+                // (P/dS are triple-buffered as well, so nothing downstream waits on dV/dK(it) soon)
+                if (it + PP_NBUF < n_y) issue_sdp(it + PP_NBUF);
                 if (DKV) {
                     const uint32_t lp = sdesc_lo_kmajor(aP), ly = sdesc_lo_mnmajor(aY2);
 #pragma unroll
@@ -1073,10 +1077,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
                                     (it > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&y_empty[st]);
-                umma_commit(&mm_done[bsel]);
-                // refill the accumulator buffer that was just drained (issuing this BEFORE dV/dK was measured slower: 379 vs
-                // 343 us — it delays mm_done, which gates the warpgroup's next P/dS write)
-                if (it + PP_NBUF < n_y) issue_sdp(it + PP_NBUF);
+                umma_commit(&mm_done[kbuf]);
             }
             umma_commit(all_done);
         }
@@ -1097,14 +1098,14 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             rowD = row_ok ? p.delta[bhoff * p.Sq + xrow] : 0.f;
         }
         if (!row_ok) rowA = -INFINITY;
-        uint8_t* myP = sP + wg * PP_PS_BYTES;
-        uint8_t* myDS = sDS + wg * PP_PS_BYTES;
         for (int it = wg; it < n_y; it += 2) {
             const int i = y0 + it;
             const int st = it % PP_STAGES;
             const int kb = it % PP_NBUF;
             const int t = it >> 1;  // this warpgroup's own tile counter
             const uint32_t tS = tmem + kb * 128, tDP = tS + 64;
+            uint8_t* myP = sP + kb * PP_PS_BYTES;
+            uint8_t* myDS = sDS + kb * PP_PS_BYTES;
             float* cA = sColA + st * TY;
             float* cD = sColD + st * TY;
             const bool full_tile = (i + 1) * TY <= rowsY;
@@ -1127,8 +1128,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             if (col_by_copy) mbar_wait(&y_full[st], (uint32_t)((it / PP_STAGES) & 1));
             mbar_wait(&s_full[kb], (uint32_t)((it / PP_NBUF) & 1));
             tc_fence_after();
-            if (t > 0) {  // this warpgroup's P/dS buffers were last read by the MMAs of its previous tile
-                mbar_wait(&mm_done[wg], (uint32_t)((t - 1) & 1));
+            if (it >= PP_NBUF) {  // P/dS buffer kb was last read by the dV/dK MMAs of tile it-3
+                mbar_wait(&mm_done[kb], (uint32_t)(((it / PP_NBUF) - 1) & 1));
                 tc_fence_after();
             }
 #pragma unroll 1
