@@ -1216,6 +1216,480 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
     }
 }
 
+// ================================================================================================
+// cross attention (Sk <= 128: ONE key tile, e.g. 2688 latent queries x 128 text keys)
+// ================================================================================================
+// The general kernels above spend a whole CTA (barrier init, TMEM alloc, pipeline fill, drain) on one query tile that
+// only has a single key tile to visit.  These two kernels keep K and V resident in shared memory and walk a CTA over a
+// RANGE of query tiles of one (b, h): grid = (ranges, B*H), sized to one CTA per SM.
+//   forward : S = Q K^T (128x128) -> full-row softmax in one go (no online rescale) -> O = P V.  The two consumer
+//             warpgroups alternate query tiles, each with its own S / O accumulators and P buffer.
+//   backward: one pass produces dQ, dK and dV (the general path needs two kernels that both recompute S and dP):
+//             S = Q K^T, dP = dO V^T -> P, dS -> dQ = dS K (per tile, double-buffered accumulator),
+//             dV += P^T dO, dK += dS^T Q (P / dS tiles re-read as MN-major A operands).  Each warpgroup takes one
+//             64-key half of every tile, so both work on the same tile at once.  Partial dK/dV of the ranges of one
+//             head are combined with fp32 atomics (or written directly when there is one range).
+struct AttnXParams {
+    CUtensorMap tmQ, tmK, tmV, tmdO;   // 128-row boxes
+    const float* key_bias;             // [B, Sk] or null
+    float* lse;                        // [B, H, Sq]   (fwd: written; bwd: read)
+    const float* delta;                // [B, H, Sq]   (bwd)
+    __nv_bfloat16* out;                // fwd: O  [B, Sq, H*64];  bwd: dQ [B, H, Sq, 64]
+    __nv_bfloat16* dk;                 // bwd, gridDim.x == 1: direct outputs [B, H, Sk, 64]
+    __nv_bfloat16* dv;
+    float* acc_dv;                     // bwd, gridDim.x > 1: fp32 accumulators, same layout
+    float* acc_dk;
+    int tiles_per_cta;
+    int B, H, Sq, Sk;
+    float scale, scale_log2;
+};
+
+constexpr int X_THREADS = 320;                 // TMA warp, MMA warp, 2 x 4 consumer warps
+constexpr int X_PS_BYTES = TILE * TILE * 2;    // 32 KB: [128 q x 128 keys] bf16 = two 128B-swizzled 64-key chunks
+constexpr uint32_t X_CHUNK = 16384;            // byte distance between the two chunks
+constexpr int XF_STAGES = 3;
+constexpr int XF_SMEM = 2 * TILE_BYTES + XF_STAGES * TILE_BYTES + 2 * X_PS_BYTES + TILE * 4 + 256 + 1024;
+constexpr int XB_STAGES = 2;
+constexpr int XB_SMEM = 2 * TILE_BYTES + XB_STAGES * 2 * TILE_BYTES + 2 * 2 * X_PS_BYTES + TILE * 4 + 256 + 1024;
+
+// MN-major A operand made of two 64-wide chunks X_CHUNK bytes apart (LBO = chunk stride)
+__device__ __forceinline__ uint32_t sdesc_lo_mnmajor_2chunk(uint32_t smem_addr) {
+    return ((smem_addr & 0x3FFFF) >> 4) | ((X_CHUNK >> 4) << 16);
+}
+
+__device__ __forceinline__ void x_load_bias(float* sBias, const float* key_bias, int b, int Sk, int k) {
+    sBias[k] = k < Sk ? (key_bias ? key_bias[(long long)b * Sk + k] * LOG2E : 0.f) : -INFINITY;
+}
+
+__global__ void __launch_bounds__(X_THREADS, 1) attn_xfwd_kernel(const __grid_constant__ AttnXParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + TILE_BYTES;
+    uint8_t* sQ = sV + TILE_BYTES;                      // [XF_STAGES]
+    uint8_t* sP = sQ + XF_STAGES * TILE_BYTES;          // [2] one per warpgroup
+    float* sBias = reinterpret_cast<float*>(sP + 2 * X_PS_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + TILE);
+    uint64_t* kv_full = bars;
+    uint64_t* q_full = bars + 1;               // [3]
+    uint64_t* q_empty = q_full + XF_STAGES;    // [3]
+    uint64_t* s_full = q_empty + XF_STAGES;    // [2]
+    uint64_t* p_full = s_full + 2;             // [2] (128 arrivals)
+    uint64_t* o_full = p_full + 2;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.y;
+    const int b = bh / p.H, h = bh % p.H;
+    const int n_qt = (p.Sq + TILE - 1) / TILE;
+    const int t0 = blockIdx.x * p.tiles_per_cta;
+    const int n = min(p.tiles_per_cta, n_qt - t0);
+    if (n <= 0) return;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmQ);
+        tma_prefetch_desc(&p.tmK);
+        tma_prefetch_desc(&p.tmV);
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < XF_STAGES; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&o_full[i], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;  // S[g] at 128*g, O[g] at 256 + 64*g
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+            tma_load_4d(sK, &p.tmK, kv_full, 0, h, 0, b);
+            tma_load_4d(sV, &p.tmV, kv_full, 0, h, 0, b);
+            for (int t = 0; t < n; ++t) {
+                const int st = t % XF_STAGES;
+                mbar_wait(&q_empty[st], (uint32_t)(((t / XF_STAGES) & 1) ^ 1));
+                mbar_expect_tx(&q_full[st], TILE_BYTES);
+                tma_load_4d(sQ + st * TILE_BYTES, &p.tmQ, &q_full[st], 0, h, (t0 + t) * TILE, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+            mbar_wait(kv_full, 0);
+            tc_fence_after();
+            const uint32_t lk = sdesc_lo_kmajor(smem_u32(sK));
+            const uint32_t lv = sdesc_lo_mnmajor(smem_u32(sV));
+            auto issue_s = [&](int t) {  // S of local tile t into the accumulator of warpgroup t & 1
+                const int st = t % XF_STAGES;
+                mbar_wait(&q_full[st], (uint32_t)((t / XF_STAGES) & 1));
+                tc_fence_after();
+                const uint32_t lq = sdesc_lo_kmajor(smem_u32(sQ + st * TILE_BYTES));
+                const uint32_t tS = tmem + (t & 1) * 128;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16_lo(tS, lq + k * SDESC_KSTEP_KMAJOR, lk + k * SDESC_KSTEP_KMAJOR, idesc_s, k > 0);
+                umma_commit(&s_full[t & 1]);
+                umma_commit(&q_empty[st]);
+            };
+            issue_s(0);
+            if (n > 1) issue_s(1);
+            for (int t = 0; t < n; ++t) {
+                const int g = t & 1;
+                mbar_wait(&p_full[g], (uint32_t)((t >> 1) & 1));  // P(t) in smem, S[g] drained
+                tc_fence_after();
+                if (t + 2 < n) issue_s(t + 2);
+                const uint32_t lp = sdesc_lo_kmajor(smem_u32(sP + g * X_PS_BYTES));
+                const uint32_t tO = tmem + 256 + g * 64;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)  // O = P . V   (contract over the 128 keys; V as MN-major B)
+                    umma_f16_lo(tO, lp + (ks >> 2) * (X_CHUNK >> 4) + (ks & 3) * SDESC_KSTEP_KMAJOR,
+                                lv + ks * SDESC_KSTEP_MNMAJOR, idesc_o, ks > 0);
+                umma_commit(&o_full[g]);
+            }
+        }
+    } else {
+        const int wg = (warp - 2) >> 2;
+        const int qd = warp & 3;
+        const int r = qd * 32 + lane;
+        const int tid256 = threadIdx.x - 64;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        if (tid256 < TILE) x_load_bias(sBias, p.key_bias, b, p.Sk, tid256);
+        named_bar_sync(1, 256);
+        const uint32_t tS = tmem + wg * 128 + lane_off;
+        const uint32_t tO = tmem + 256 + wg * 64 + lane_off;
+        uint8_t* myP = sP + wg * X_PS_BYTES;
+        for (int t = wg; t < n; t += 2) {
+            const uint32_t par = (uint32_t)((t >> 1) & 1);
+            mbar_wait(&s_full[wg], par);
+            tc_fence_after();
+            // pass 1: row maximum in the log2 domain
+            float m = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t sv[32];
+                tmem_ld32(tS + c * 32, sv);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) m = fmaxf(m, fmaf(__uint_as_float(sv[e]), p.scale_log2, sBias[c * 32 + e]));
+            }
+            const float m_use = (m == -INFINITY) ? 0.f : m;
+            float l = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t sv[32];
+                tmem_ld32(tS + c * 32, sv);
+                tmem_ld_wait();
+                float pe[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    pe[e] = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, sBias[c * 32 + e]) - m_use);
+                    l += pe[e];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint4 w = make_uint4(pack_bf16x2(pe[u * 8], pe[u * 8 + 1]), pack_bf16x2(pe[u * 8 + 2], pe[u * 8 + 3]),
+                                         pack_bf16x2(pe[u * 8 + 4], pe[u * 8 + 5]), pack_bf16x2(pe[u * 8 + 6], pe[u * 8 + 7]));
+                    *reinterpret_cast<uint4*>(myP + (c >> 1) * X_CHUNK + sw128_off(r, (c & 1) * 4 + u)) = w;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&p_full[wg]);
+            const int qrow = (t0 + t) * TILE + r;
+            const float inv_l = 1.f / l;
+            if (qrow < p.Sq) p.lse[((long long)b * p.H + h) * p.Sq + qrow] = m_use * LN2 + logf(l);
+            mbar_wait(&o_full[wg], par);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tO + c * 32, v);
+                tmem_ld_wait();
+                if (qrow < p.Sq) {
+                    __nv_bfloat16* o = p.out + ((long long)b * p.Sq + qrow) * (p.H * HD) + h * HD + c * 32;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 w = make_uint4(
+                            pack_bf16x2(__uint_as_float(v[u * 8]) * inv_l, __uint_as_float(v[u * 8 + 1]) * inv_l),
+                            pack_bf16x2(__uint_as_float(v[u * 8 + 2]) * inv_l, __uint_as_float(v[u * 8 + 3]) * inv_l),
+                            pack_bf16x2(__uint_as_float(v[u * 8 + 4]) * inv_l, __uint_as_float(v[u * 8 + 5]) * inv_l),
+                            pack_bf16x2(__uint_as_float(v[u * 8 + 6]) * inv_l, __uint_as_float(v[u * 8 + 7]) * inv_l));
+                        *reinterpret_cast<uint4*>(o + u * 8) = w;
+                    }
+                }
+            }
+            tc_fence_before();  // O[wg] / S[wg] reads are ordered before this warpgroup's next p_full arrival
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+__global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_constant__ AttnXParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + TILE_BYTES;
+    uint8_t* sQ = sV + TILE_BYTES;                       // stage s: Q at + s*32K, dO right after
+    uint8_t* sP = sQ + XB_STAGES * 2 * TILE_BYTES;       // buffer j: P at + j*64K, dS right after
+    float* sBias = reinterpret_cast<float*>(sP + 2 * 2 * X_PS_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + TILE);
+    uint64_t* kv_full = bars;
+    uint64_t* q_full = bars + 1;               // [2]
+    uint64_t* q_empty = q_full + XB_STAGES;    // [2]
+    uint64_t* s_full = q_empty + XB_STAGES;    // S and dP of the current tile
+    uint64_t* ds_full = s_full + 1;            // 256 arrivals: P/dS written, S/dP drained
+    uint64_t* mm_done = ds_full + 1;           // [2] dQ/dV/dK MMAs of the tile using P/dS buffer j retired (dQ[j] ready)
+    uint64_t* dq_free = mm_done + 2;           // [2] 256 arrivals: dQ[j] read back
+    uint64_t* all_done = dq_free + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.y;
+    const int b = bh / p.H, h = bh % p.H;
+    const int n_qt = (p.Sq + TILE - 1) / TILE;
+    const int t0 = blockIdx.x * p.tiles_per_cta;
+    const int n = min(p.tiles_per_cta, n_qt - t0);
+    if (n <= 0) return;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmQ);
+        tma_prefetch_desc(&p.tmK);
+        tma_prefetch_desc(&p.tmV);
+        tma_prefetch_desc(&p.tmdO);
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < XB_STAGES; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(ds_full, 256);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&mm_done[i], 1);
+            mbar_init(&dq_free[i], 256);
+        }
+        mbar_init(all_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    // S at 0 (128 key columns), dP at 128, dV at 256, dK at 320, dQ[j] at 384 + 64*j
+    const uint32_t tDV = tmem + 256, tDK = tmem + 320;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+            tma_load_4d(sK, &p.tmK, kv_full, 0, h, 0, b);
+            tma_load_4d(sV, &p.tmV, kv_full, 0, h, 0, b);
+            for (int t = 0; t < n; ++t) {
+                const int st = t % XB_STAGES;
+                mbar_wait(&q_empty[st], (uint32_t)(((t / XB_STAGES) & 1) ^ 1));
+                mbar_expect_tx(&q_full[st], 2 * TILE_BYTES);
+                tma_load_4d(sQ + st * 2 * TILE_BYTES, &p.tmQ, &q_full[st], 0, h, (t0 + t) * TILE, b);
+                tma_load_4d(sQ + st * 2 * TILE_BYTES + TILE_BYTES, &p.tmdO, &q_full[st], 0, h, (t0 + t) * TILE, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);
+            constexpr uint32_t idesc_kv = make_idesc_bf16(128, 64, 1, 1);
+            mbar_wait(kv_full, 0);
+            tc_fence_after();
+            const uint32_t lk = sdesc_lo_kmajor(smem_u32(sK)), lv = sdesc_lo_kmajor(smem_u32(sV));
+            const uint32_t lk_mn = sdesc_lo_mnmajor(smem_u32(sK));
+            auto issue_sdp = [&](int t) {
+                const int st = t % XB_STAGES;
+                mbar_wait(&q_full[st], (uint32_t)((t / XB_STAGES) & 1));
+                tc_fence_after();
+                const uint32_t aQ = smem_u32(sQ + st * 2 * TILE_BYTES);
+                const uint32_t lq = sdesc_lo_kmajor(aQ), ldo = sdesc_lo_kmajor(aQ + TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16_lo(tmem, lq + k * SDESC_KSTEP_KMAJOR, lk + k * SDESC_KSTEP_KMAJOR, idesc_s, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16_lo(tmem + 128, ldo + k * SDESC_KSTEP_KMAJOR, lv + k * SDESC_KSTEP_KMAJOR, idesc_s, k > 0);
+                umma_commit(s_full);
+            };
+            issue_sdp(0);
+            for (int t = 0; t < n; ++t) {
+                const int j = t & 1;
+                const int st = t % XB_STAGES;
+                mbar_wait(ds_full, (uint32_t)(t & 1));  // P/dS(t) in buffer j, S/dP drained
+                tc_fence_after();
+                if (t + 1 < n) issue_sdp(t + 1);  // refill first: it heads the consumers' chain
+                if (t >= 2) {
+                    mbar_wait(&dq_free[j], (uint32_t)(((t >> 1) - 1) & 1));
+                    tc_fence_after();
+                }
+                const uint32_t aP = smem_u32(sP + j * 2 * X_PS_BYTES), aDS = aP + X_PS_BYTES;
+                const uint32_t aQ = smem_u32(sQ + st * 2 * TILE_BYTES), aDO = aQ + TILE_BYTES;
+                const uint32_t tDQ = tmem + 384 + j * 64;
+                {
+                    const uint32_t lds = sdesc_lo_kmajor(aDS);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)  // dQ = dS . K   (K as MN-major B)
+                        umma_f16_lo(tDQ, lds + (ks >> 2) * (X_CHUNK >> 4) + (ks & 3) * SDESC_KSTEP_KMAJOR,
+                                    lk_mn + ks * SDESC_KSTEP_MNMAJOR, idesc_q, ks > 0);
+                }
+                {
+                    const uint32_t lpt = sdesc_lo_mnmajor_2chunk(aP), ldo = sdesc_lo_mnmajor(aDO);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)  // dV += P^T . dO   (contract over the 128 queries)
+                        umma_f16_lo(tDV, lpt + ks * SDESC_KSTEP_MNMAJOR, ldo + ks * SDESC_KSTEP_MNMAJOR, idesc_kv,
+                                    (t > 0 || ks > 0) ? 1u : 0u);
+                }
+                {
+                    const uint32_t ldst = sdesc_lo_mnmajor_2chunk(aDS), lq = sdesc_lo_mnmajor(aQ);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)  // dK += dS^T . Q
+                        umma_f16_lo(tDK, ldst + ks * SDESC_KSTEP_MNMAJOR, lq + ks * SDESC_KSTEP_MNMAJOR, idesc_kv,
+                                    (t > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&q_empty[st]);
+                umma_commit(&mm_done[j]);
+            }
+            umma_commit(all_done);
+        }
+    } else {
+        const int wg = (warp - 2) >> 2;   // warpgroup g owns keys [64 g, 64 g + 64) of every tile
+        const int qd = warp & 3;
+        const int r = qd * 32 + lane;
+        const int tid256 = threadIdx.x - 64;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const long long bhoff = (long long)b * p.H + h;
+        if (tid256 < TILE) x_load_bias(sBias, p.key_bias, b, p.Sk, tid256);
+        named_bar_sync(1, 256);
+        const uint32_t tS = tmem + lane_off + wg * 64, tDP = tS + 128;
+        const float* myBias = sBias + wg * 64;
+
+        auto dq_epilogue = [&](int tt) {  // dQ rows of tile tt: this warpgroup writes columns [32 wg, 32 wg + 32)
+            const int j = tt & 1;
+            mbar_wait(&mm_done[j], (uint32_t)((tt >> 1) & 1));
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld32(tmem + lane_off + 384 + j * 64 + wg * 32, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&dq_free[j]);
+            const int qrow = (t0 + tt) * TILE + r;
+            if (qrow < p.Sq) {
+                __nv_bfloat16* dst = p.out + (bhoff * p.Sq + qrow) * HD + wg * 32;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint4 w = make_uint4(
+                        pack_bf16x2(__uint_as_float(v[u * 8]) * p.scale, __uint_as_float(v[u * 8 + 1]) * p.scale),
+                        pack_bf16x2(__uint_as_float(v[u * 8 + 2]) * p.scale, __uint_as_float(v[u * 8 + 3]) * p.scale),
+                        pack_bf16x2(__uint_as_float(v[u * 8 + 4]) * p.scale, __uint_as_float(v[u * 8 + 5]) * p.scale),
+                        pack_bf16x2(__uint_as_float(v[u * 8 + 6]) * p.scale, __uint_as_float(v[u * 8 + 7]) * p.scale));
+                    *reinterpret_cast<uint4*>(dst + u * 8) = w;
+                }
+            }
+        };
+
+        for (int t = 0; t < n; ++t) {
+            const int j = t & 1;
+            const int qrow = (t0 + t) * TILE + r;
+            const bool row_ok = qrow < p.Sq;
+            const float rowA = row_ok ? -p.lse[bhoff * p.Sq + qrow] * LOG2E : -INFINITY;
+            const float rowD = row_ok ? p.delta[bhoff * p.Sq + qrow] : 0.f;
+            uint8_t* myP = sP + j * 2 * X_PS_BYTES + wg * X_CHUNK;
+            uint8_t* myDS = myP + X_PS_BYTES;
+            mbar_wait(s_full, (uint32_t)(t & 1));
+            tc_fence_after();
+            // (P/dS buffer j was last read by the MMAs of tile t-2: dq_epilogue(t-2) already waited on mm_done[j])
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t sv[32], dv[32];
+                tmem_ld32(tS + c * 32, sv);
+                tmem_ld32(tDP + c * 32, dv);
+                tmem_ld_wait();
+                float pe[32], ds[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float pp = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, rowA + myBias[c * 32 + e]));
+                    pe[e] = pp;
+                    ds[e] = pp * (__uint_as_float(dv[e]) - rowD);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t off = sw128_off(r, c * 4 + u);
+                    *reinterpret_cast<uint4*>(myP + off) =
+                        make_uint4(pack_bf16x2(pe[u * 8], pe[u * 8 + 1]), pack_bf16x2(pe[u * 8 + 2], pe[u * 8 + 3]),
+                                   pack_bf16x2(pe[u * 8 + 4], pe[u * 8 + 5]), pack_bf16x2(pe[u * 8 + 6], pe[u * 8 + 7]));
+                    *reinterpret_cast<uint4*>(myDS + off) =
+                        make_uint4(pack_bf16x2(ds[u * 8], ds[u * 8 + 1]), pack_bf16x2(ds[u * 8 + 2], ds[u * 8 + 3]),
+                                   pack_bf16x2(ds[u * 8 + 4], ds[u * 8 + 5]), pack_bf16x2(ds[u * 8 + 6], ds[u * 8 + 7]));
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(ds_full);
+            if (t >= 1) dq_epilogue(t - 1);
+        }
+        dq_epilogue(n - 1);
+        // ---- dV (warpgroup 0) / dK (warpgroup 1): thread r owns key row r
+        mbar_wait(all_done, 0);
+        tc_fence_after();
+        const bool key_ok = r < p.Sk;
+        const long long ro = (bhoff * p.Sk + r) * HD;
+        const float osc = wg == 0 ? 1.f : p.scale;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32((wg == 0 ? tDV : tDK) + lane_off + c * 32, v);
+            tmem_ld_wait();
+            if (key_ok) {
+                if (gridDim.x > 1) {
+                    float* facc = (wg == 0 ? p.acc_dv : p.acc_dk) + ro + c * 32;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) atomicAdd(facc + e, __uint_as_float(v[e]) * osc);
+                } else {
+                    __nv_bfloat16* dst = (wg == 0 ? p.dv : p.dk) + ro + c * 32;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 w = make_uint4(
+                            pack_bf16x2(__uint_as_float(v[u * 8]) * osc, __uint_as_float(v[u * 8 + 1]) * osc),
+                            pack_bf16x2(__uint_as_float(v[u * 8 + 2]) * osc, __uint_as_float(v[u * 8 + 3]) * osc),
+                            pack_bf16x2(__uint_as_float(v[u * 8 + 4]) * osc, __uint_as_float(v[u * 8 + 5]) * osc),
+                            pack_bf16x2(__uint_as_float(v[u * 8 + 6]) * osc, __uint_as_float(v[u * 8 + 7]) * osc));
+                        *reinterpret_cast<uint4*>(dst + u * 8) = w;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
     long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
@@ -1278,6 +1752,23 @@ extern "C" int b2d_attn_fwd(const void* q, const void* k, const void* v, const f
     // the MMA round trip, 2 CTAs/SM; 120 us at S=2688, H=32, at which point the MUFU ex2 unit is ~85 % busy) and "classic"
     // (B2D_ATTN_FWD=classic; 128-wide tiles, 2 CTAs/SM interleaving MMA and softmax, 125 us; used when Sk <= 128)
     static const bool force_classic = []() { const char* e = getenv("B2D_ATTN_FWD"); return e && e[0] == 'c'; }();
+    static const bool cross_general = []() { const char* e = getenv("B2D_ATTN_CROSS"); return e && e[0] == 'g'; }();
+    if (Sk <= TILE && !cross_general) {
+        // single key tile (cross attention): K/V-resident kernel walking a range of query tiles per CTA
+        AttnXParams x;
+        memset(&x, 0, sizeof(x));
+        x.tmQ = p.tmQ; x.tmK = p.tmK; x.tmV = p.tmV;
+        x.key_bias = key_bias; x.lse = lse; x.out = (__nv_bfloat16*)out;
+        x.B = B; x.H = H; x.Sq = Sq; x.Sk = Sk; x.scale = scale; x.scale_log2 = scale * LOG2E;
+        const int n_qt = (Sq + TILE - 1) / TILE;
+        const int ranges = min(n_qt, max(1, device_sm_count() / (B * H)));
+        x.tiles_per_cta = (n_qt + ranges - 1) / ranges;
+        if ((rc = set_smem((const void*)attn_xfwd_kernel, XF_SMEM, "attn_xfwd"))) return rc;
+        attn_xfwd_kernel<<<dim3((n_qt + x.tiles_per_cta - 1) / x.tiles_per_cta, B * H), X_THREADS, XF_SMEM,
+                           reinterpret_cast<cudaStream_t>(stream)>>>(x);
+        B2D_CHECK_LAUNCH("attn_xfwd");
+        return 0;
+    }
     if ((rc = set_smem((const void*)attn_fwd_kernel, FWD_SMEM, "attn_fwd"))) return rc;
     if ((rc = set_smem((const void*)attn_fwd_db_kernel, FDB_SMEM, "attn_fwd_db"))) return rc;
     dim3 grid((Sq + TILE - 1) / TILE, B * H);
@@ -1312,6 +1803,36 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
     if ((rc = make_head_map(&mKy, k, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64, TY))) return rc;
     if ((rc = make_head_map(&mVy, v, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64, TY))) return rc;
     if ((rc = make_head_map(&mdOy, dout, B, H, Sq, 64, (long long)H * 64, (long long)Sq * H * 64, TY))) return rc;
+    static const bool cross_general = []() { const char* e = getenv("B2D_ATTN_CROSS"); return e && e[0] == 'g'; }();
+    if (Sk <= TILE && !cross_general) {
+        // single key tile (cross attention): one fused pass for dQ, dK, dV
+        AttnXParams x;
+        memset(&x, 0, sizeof(x));
+        x.tmQ = mQ; x.tmK = mK; x.tmV = mV; x.tmdO = mdO;
+        x.key_bias = key_bias; x.lse = const_cast<float*>(lse); x.delta = delta_ws;
+        x.out = (__nv_bfloat16*)dq; x.dk = (__nv_bfloat16*)dk; x.dv = (__nv_bfloat16*)dv;
+        x.B = B; x.H = H; x.Sq = Sq; x.Sk = Sk; x.scale = scale; x.scale_log2 = scale * LOG2E;
+        const int n_qt = (Sq + TILE - 1) / TILE;
+        const int ranges = min(n_qt, max(1, device_sm_count() / (B * H)));
+        x.tiles_per_cta = (n_qt + ranges - 1) / ranges;
+        const int gx = (n_qt + x.tiles_per_cta - 1) / x.tiles_per_cta;
+        const long long n_kv = (long long)B * H * Sk * HD;
+        if (gx > 1) {
+            x.acc_dv = delta_ws + 2LL * B * H * Sq;
+            x.acc_dk = x.acc_dv + n_kv;
+            cudaError_t e = cudaMemsetAsync(x.acc_dv, 0, 2 * n_kv * sizeof(float), st);
+            if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "attn_bwd memset: %s", cudaGetErrorString(e));
+        }
+        if ((rc = set_smem((const void*)attn_xbwd_kernel, XB_SMEM, "attn_xbwd"))) return rc;
+        attn_xbwd_kernel<<<dim3(gx, B * H), X_THREADS, XB_SMEM, st>>>(x);
+        B2D_CHECK_LAUNCH("attn_xbwd");
+        if (gx > 1) {
+            f32_to_bf16_kernel<<<(unsigned)((n_kv / 4 + 255) / 256), 256, 0, st>>>(x.acc_dv, (__nv_bfloat16*)dv, n_kv);
+            f32_to_bf16_kernel<<<(unsigned)((n_kv / 4 + 255) / 256), 256, 0, st>>>(x.acc_dk, (__nv_bfloat16*)dk, n_kv);
+            B2D_CHECK_LAUNCH("attn_xbwd(convert)");
+        }
+        return 0;
+    }
     AttnBwdParams p;
     memset(&p, 0, sizeof(p));
     p.key_bias = key_bias; p.lse = lse; p.delta = delta_ws; p.nlse2 = delta_ws + (long long)B * H * Sq;

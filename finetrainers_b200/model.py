@@ -477,6 +477,7 @@ class B200LTXTransformer(nn.Module):
             sst = e["sst"]
             h_in, n1 = ws["h"][l], ws["n1"][l]
             # K5: RMSNorm + modulate (shift_msa = row 0, scale_msa = row 1)
+            ops.CONTEXT = "f.self"
             ops.norm_modulate_fwd(h_in, n1, sst[0], temb[:, 0:], sst[1], temb[:, d:], 6 * d, R, d, S, cfg.norm_eps)
             # K6: fused QKV (+LoRA)
             self._lin(n1, e["Wqkv"], e["bqkv"], ws["qkv"][l], R, 3 * d, d,
@@ -493,6 +494,7 @@ class B200LTXTransformer(nn.Module):
                       epi=ops.EPI_GATE_RES, res=h_in, gate_table=sst[2], gate_temb=temb[:, 2 * d:], temb_stride=6 * d,
                       rows_per_sample=S)
             # K10: cross attention (no pre-norm, no gate)
+            ops.CONTEXT = "f.cross"
             h1 = ws["h1"][l]
             self._lin(h1, e["Wq2"], e["bq2"], ws["q2"][l], R, d, d,
                       lora=(e["Ab_q2"], e["Bb_q2"], ws["u_q2"][l], 1) if rp else None)
@@ -506,6 +508,7 @@ class B200LTXTransformer(nn.Module):
                       lora=(e["Ab_o2"], e["Bb_o2"], ws["u_o2"][l], 1) if rp else None,
                       epi=ops.EPI_GATE_RES, res=h1)
             # K11/K12: norm2 + modulate (rows 3,4), FFN with GELU epilogue, gated residual (row 5)
+            ops.CONTEXT = "f.ffn"
             h2 = ws["h2"][l]
             ops.norm_modulate_fwd(h2, ws["n2"], sst[3], temb[:, 3 * d:], sst[4], temb[:, 4 * d:], 6 * d, R, d, S,
                                   cfg.norm_eps)
@@ -513,10 +516,12 @@ class B200LTXTransformer(nn.Module):
                      out2=ws["ffpre"][l], tag="ffn_up")
             ops.gemm(ws["f"], e["W2"], ws["h"][l + 1], M=R, N=d, K=cfg.ffn_mult * d, bias=e["b2"], epi=ops.EPI_GATE_RES,
                      res=h2, gate_table=sst[5], gate_temb=temb[:, 5 * d:], temb_stride=6 * d, rows_per_sample=S)
+        ops.CONTEXT = "f.head"
         # K13: final LayerNorm + modulate (table rows 0 = shift, 1 = scale; embedded_timestep), proj_out
         t2 = self.scale_shift_table.data
         ops.norm_modulate_fwd(ws["h"][nl], ws["y"], t2[0], ws["embedded"], t2[1], ws["embedded"], d, R, d, S, 1e-6, True)
         ops.gemm(ws["y"], self.proj_out.weight, ws["pred"], M=R, N=cfg.out_channels, K=d, bias=self.proj_out.bias)
+        ops.CONTEXT = ""
         return ws["pred"].view(B, S, cfg.out_channels)
 
     # ------------------------------------------------------------------------------------------------
@@ -599,11 +604,13 @@ class B200LTXTransformer(nn.Module):
             sst = e["sst"]
             dh2, dq2, dkv2, dyo, dqkv = ws["dy_o2"][l], ws["dy_q2"][l], ws["dy_kv2"][l], ws["dy_o"][l], ws["dy_qkv"][l]
             # ---- FFN: dfp = (g W2) * gelu'(pre) ; dn2 = dfp W1 ; dh2 = dh + norm_bwd(dn2; h2, scale_mlp=row 4)
+            ops.CONTEXT = "b.ffn"
             ops.gemm(g, e["W2"], ws["dwide"], M=R, N=cfg.ffn_mult * d, K=d, b_mn=True, epi=ops.EPI_MUL_DGELU,
                      aux=ws["ffpre"][l])
             ops.gemm(ws["dwide"], e["W1"], ws["dn"], M=R, N=d, K=cfg.ffn_mult * d, b_mn=True)
             ops.norm_modulate_bwd(ws["dn"], ws["h2"][l], dh, dh2, sst[4], temb[:, 4 * d:], 6 * d, R, d, S, cfg.norm_eps)
             # ---- cross attention out-proj (no gate): da2 = dh2 W_o2 + du A
+            ops.CONTEXT = "b.cross"
             du = self._lora_du(dh2, ws["du_o2"][l], e, "o2", R, d, 1)
             ops.gemm(dh2, e["Wo2"], ws["da"], M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_o2"], K2=rp)
             ops.attn_bwd(ws["q2h"][l], ws["k2h"][l], ws["v2h"][l], key_bias, ws["ao2"][l], ws["da"], ws["lse2"][l],
@@ -620,6 +627,7 @@ class B200LTXTransformer(nn.Module):
                      epi=ops.EPI_GATE_RES, res=dh2, gate2_table=sst[2], gate2_temb=temb[:, 2 * d:], out2=dyo,
                      temb_stride=6 * d, rows_per_sample=S)
             # ---- self attention out-proj (gated): dattn = g W_o + du A
+            ops.CONTEXT = "b.self"
             du = self._lora_du(dyo, ws["du_o"][l], e, "o", R, d, 1)
             ops.gemm(dyo, e["Wo"], ws["da"], M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_o"], K2=rp)
             ops.attn_bwd(ws["qh"][l], ws["kh"][l], ws["vh"][l], None, ws["ao"][l], ws["da"], ws["lse"][l], ws["delta"],
@@ -639,4 +647,6 @@ class B200LTXTransformer(nn.Module):
             ops.norm_modulate_bwd(ws["dn"], ws["h"][l], dh, dh, sst[1], temb[:, d:], 6 * d, R, d, S, cfg.norm_eps,
                                   gate2_tab=prev[5] if l > 0 else None, gate2_emb=temb[:, 5 * d:] if l > 0 else None,
                                   out2=g if l > 0 else None)
+        ops.CONTEXT = "b.wgrad"
         self._lora_wgrads_all(ws, R, RL)
+        ops.CONTEXT = ""

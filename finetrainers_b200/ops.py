@@ -16,6 +16,7 @@ EPI_STORE, EPI_GELU, EPI_SILU, EPI_GATE_RES, EPI_MUL_DGELU, EPI_F32_ATOMIC, EPI_
 LAUNCH_COUNT = 0  # number of libb2d kernels launched (bench.py reports it as gpu_launches)
 TIMING = False    # when True every wrapper brackets its launch with CUDA events on the current stream
 KERNEL_TIMES = {}  # tag -> [(start_event, end_event), ...]
+CONTEXT = ""      # optional call-site label set by the model (profiling only): tags become "<CONTEXT>/<tag>"
 
 
 class _Timed:
@@ -33,7 +34,7 @@ class _Timed:
         if TIMING:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            KERNEL_TIMES.setdefault(self.tag, []).append((self.e0, e1))
+            KERNEL_TIMES.setdefault(f"{CONTEXT}/{self.tag}" if CONTEXT else self.tag, []).append((self.e0, e1))
 
 
 def collect_kernel_times():
@@ -175,9 +176,15 @@ def attn_bwd(q, k, v, key_bias, out, dout, lse, delta_ws, dq, dk, dv, B, H, Sq, 
         check(_l.load().b2d_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(key_bias), _ptr(out), _ptr(dout), _ptr(lse),
                                      _ptr(delta_ws), _ptr(dq), _ptr(dk), _ptr(dv), B, H, Sq, Sk, C.c_float(scale),
                                      _stream()), "attn_bwd")
-    # kernels launched: delta + dK/dV + dQ, plus two fp32->bf16 converts when the cross-attention split path runs
-    split = (B * H * ((Sk + 127) // 128) < 96) and Sk <= 512 and ((Sq + 63) // 64) >= 8
-    _count(5 if split else 3)
+    if Sk <= 128:
+        # single key tile: delta + ONE fused dQ/dK/dV kernel, plus two fp32->bf16 converts when a head's query range is
+        # spread over several CTAs
+        n_qt = (Sq + 127) // 128
+        _count(4 if min(n_qt, max(1, 148 // (B * H))) > 1 else 2)
+    else:
+        # delta + dK/dV + dQ, plus two fp32->bf16 converts when the few-key-tiles split path runs
+        split = (B * H * ((Sk + 127) // 128) < 96) and Sk <= 512 and ((Sq + 63) // 64) >= 8
+        _count(5 if split else 3)
 
 
 def prep_noise_pack(latents, noise, mean, std, sigma, sigma_ff, x_t, target, B, Cc, F, HW):

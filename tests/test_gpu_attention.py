@@ -36,7 +36,8 @@ def test_reference_attention_kat_through_provider_hook():
 
 
 @pytest.mark.parametrize("B,H,Sq,Sk,bias", [(1, 32, 2688, 2688, False), (2, 4, 2688, 128, True), (1, 2, 200, 72, True),
-                                            (1, 2, 128, 128, False), (1, 3, 1, 1, False), (2, 2, 130, 257, True)])
+                                            (1, 2, 128, 128, False), (1, 3, 1, 1, False), (2, 2, 130, 257, True),
+                                            (1, 32, 2688, 128, True), (5, 32, 300, 128, True), (3, 2, 1000, 100, False)])
 def test_attention_fwd_bwd_shapes(B, H, Sq, Sk, bias):
     from finetrainers_b200 import ops
     torch.manual_seed(0)

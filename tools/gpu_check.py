@@ -290,7 +290,7 @@ def check_elem():
 def check_attn():
     torch.manual_seed(0)
     cases = [(2, 8, 256, 256, False), (1, 32, 2688, 2688, False), (2, 4, 2688, 128, True), (1, 2, 200, 72, True),
-             (1, 2, 128, 128, False)]
+             (1, 2, 128, 128, False), (1, 32, 2688, 128, True), (5, 32, 300, 128, True), (3, 2, 1000, 100, False)]
     for (B_, H, Sq, Sk, use_bias) in cases:
         q = rnd(B_, H, Sq, 64); k = rnd(B_, H, Sk, 64); v = rnd(B_, H, Sk, 64)
         bias = None
@@ -344,6 +344,24 @@ def check_attn():
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
             print(f"[time] {name} S=2688 H=32: {ms*1e3:.1f} us  {flops/ms/1e9:.0f} TFLOP/s", flush=True)
+        except Exception as e:
+            print("EXC timing", name, e)
+    # cross attention at the LTX shape: 2688 queries x 128 text keys, key bias
+    L = 128
+    kc = rnd(B_, H, L, 64); vc = rnd(B_, H, L, 64); dkc = torch.zeros_like(kc); dvc = torch.zeros_like(vc)
+    biasc = torch.zeros(B_, L, device=dev); biasc[:, 77:] = -10000.0
+    wsc = torch.zeros(ops.attn_bwd_ws_floats(B_, H, S, L), device=dev)
+    for fn, name in ((lambda: ops.attn_fwd(q, kc, vc, biasc, out, lse, B_, H, S, L, 0.125), "cross attn_fwd"),
+                     (lambda: ops.attn_bwd(q, kc, vc, biasc, out, dout, lse, wsc, dq, dkc, dvc, B_, H, S, L, 0.125), "cross attn_bwd")):
+        try:
+            for _ in range(3):
+                fn()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            print(f"[time] {name} Sq=2688 Sk=128 H=32: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us", flush=True)
         except Exception as e:
             print("EXC timing", name, e)
     qt = q.clone().requires_grad_(True)
