@@ -1233,12 +1233,13 @@ struct AttnXParams {
     CUtensorMap tmQ, tmK, tmV, tmdO;   // 128-row boxes
     const float* key_bias;             // [B, Sk] or null
     float* lse;                        // [B, H, Sq]   (fwd: written; bwd: read)
-    const float* delta;                // [B, H, Sq]   (bwd)
+    const __nv_bfloat16* o;            // bwd: forward output O [B, Sq, H*64] (delta = rowsum(O * dO) is formed in-kernel)
     __nv_bfloat16* out;                // fwd: O  [B, Sq, H*64];  bwd: dQ [B, H, Sq, 64]
     __nv_bfloat16* dk;                 // bwd, gridDim.x == 1: direct outputs [B, H, Sk, 64]
     __nv_bfloat16* dv;
-    float* acc_dv;                     // bwd, gridDim.x > 1: fp32 accumulators, same layout
+    float* acc_dv;                     // bwd, gridDim.x > 1: fp32 accumulators, same layout (zeroed by the host)
     float* acc_dk;
+    unsigned int* tickets;             // bwd, gridDim.x > 1: [B*H] arrival counters (zeroed by the host)
     int tiles_per_cta;
     int B, H, Sq, Sk;
     float scale, scale_log2;
@@ -1615,11 +1616,32 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_co
             const int qrow = (t0 + t) * TILE + r;
             const bool row_ok = qrow < p.Sq;
             const float rowA = row_ok ? -p.lse[bhoff * p.Sq + qrow] * LOG2E : -INFINITY;
-            const float rowD = row_ok ? p.delta[bhoff * p.Sq + qrow] : 0.f;
+            // delta = sum_d O[q,d] dO[q,d]: the O row comes straight from global (issued before the wait below), the dO
+            // row from the tile the TMA already staged (s_full implies it has landed; it stays until the tile's last MMA)
+            uint4 o4[8];
+            {
+                const uint4* og = reinterpret_cast<const uint4*>(
+                    p.o + ((long long)b * p.Sq + (row_ok ? qrow : 0)) * (p.H * HD) + h * HD);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) o4[u] = __ldg(og + u);
+            }
             uint8_t* myP = sP + j * 2 * X_PS_BYTES + wg * X_CHUNK;
             uint8_t* myDS = myP + X_PS_BYTES;
             mbar_wait(s_full, (uint32_t)(t & 1));
             tc_fence_after();
+            float rowD = 0.f;
+            {
+                const uint8_t* sdO = sQ + (t % XB_STAGES) * 2 * TILE_BYTES + TILE_BYTES;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint4 d4 = *reinterpret_cast<const uint4*>(sdO + sw128_off(r, u));
+                    rowD += bf16_lo(o4[u].x) * bf16_lo(d4.x) + bf16_hi(o4[u].x) * bf16_hi(d4.x) +
+                            bf16_lo(o4[u].y) * bf16_lo(d4.y) + bf16_hi(o4[u].y) * bf16_hi(d4.y) +
+                            bf16_lo(o4[u].z) * bf16_lo(d4.z) + bf16_hi(o4[u].z) * bf16_hi(d4.z) +
+                            bf16_lo(o4[u].w) * bf16_lo(d4.w) + bf16_hi(o4[u].w) * bf16_hi(d4.w);
+                }
+                if (!row_ok) rowD = 0.f;
+            }
             // (P/dS buffer j was last read by the MMAs of tile t-2: dq_epilogue(t-2) already waited on mm_done[j])
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
@@ -1651,24 +1673,21 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_co
             if (t >= 1) dq_epilogue(t - 1);
         }
         dq_epilogue(n - 1);
-        // ---- dV (warpgroup 0) / dK (warpgroup 1): thread r owns key row r
+        // ---- dV (warpgroup 0) / dK (warpgroup 1): thread r owns key row r of the accumulator
         mbar_wait(all_done, 0);
         tc_fence_after();
         const bool key_ok = r < p.Sk;
-        const long long ro = (bhoff * p.Sk + r) * HD;
         const float osc = wg == 0 ? 1.f : p.scale;
+        const uint32_t tacc = (wg == 0 ? tDV : tDK) + lane_off;
+        const long long head_off = bhoff * p.Sk * HD;
+        if (gridDim.x == 1) {
+            __nv_bfloat16* dst = (wg == 0 ? p.dv : p.dk) + head_off + (long long)r * HD;
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld32((wg == 0 ? tDV : tDK) + lane_off + c * 32, v);
-            tmem_ld_wait();
-            if (key_ok) {
-                if (gridDim.x > 1) {
-                    float* facc = (wg == 0 ? p.acc_dv : p.acc_dk) + ro + c * 32;
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) atomicAdd(facc + e, __uint_as_float(v[e]) * osc);
-                } else {
-                    __nv_bfloat16* dst = (wg == 0 ? p.dv : p.dk) + ro + c * 32;
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tacc + c * 32, v);
+                tmem_ld_wait();
+                if (key_ok) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         uint4 w = make_uint4(
@@ -1676,7 +1695,54 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_co
                             pack_bf16x2(__uint_as_float(v[u * 8 + 2]) * osc, __uint_as_float(v[u * 8 + 3]) * osc),
                             pack_bf16x2(__uint_as_float(v[u * 8 + 4]) * osc, __uint_as_float(v[u * 8 + 5]) * osc),
                             pack_bf16x2(__uint_as_float(v[u * 8 + 6]) * osc, __uint_as_float(v[u * 8 + 7]) * osc));
-                        *reinterpret_cast<uint4*>(dst + u * 8) = w;
+                        *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = w;
+                    }
+                }
+            }
+        } else {
+            // Several CTAs share this head: combine with fp32 atomics.  One thread per ROW would scatter every warp-wide
+            // atomic over 32 lines, so the tile is first transposed through shared memory (the P/dS buffers are idle now;
+            // 16-byte units XOR-swizzled by row) and then added with coalesced 16-byte vector atomics.
+            const int tid128 = ((warp - 2) & 3) * 32 + lane;
+            uint8_t* sT = sP + wg * X_PS_BYTES;  // [128 rows x 64 fp32] = 32 KB per warpgroup
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tacc + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int k = c * 8 + u;
+                    *reinterpret_cast<float4*>(sT + r * 256 + ((k ^ (r & 15)) << 4)) =
+                        make_float4(__uint_as_float(v[u * 4]) * osc, __uint_as_float(v[u * 4 + 1]) * osc,
+                                    __uint_as_float(v[u * 4 + 2]) * osc, __uint_as_float(v[u * 4 + 3]) * osc);
+                }
+            }
+            named_bar_sync(2 + wg, 128);
+            float* facc = (wg == 0 ? p.acc_dv : p.acc_dk) + head_off;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int idx = i * 128 + tid128;  // float4 index inside the [128 x 64] tile
+                const int row = idx >> 4, k = idx & 15;
+                if (row < p.Sk) {
+                    const float4 val = *reinterpret_cast<const float4*>(sT + row * 256 + ((k ^ (row & 15)) << 4));
+                    atomicAdd(reinterpret_cast<float4*>(facc) + idx, val);
+                }
+            }
+            // the CTA that arrives last for this head rounds the accumulated dV / dK to bf16 (no separate convert launches)
+            __threadfence();
+            named_bar_sync(1, 256);
+            if (tid256 == 0) tmem_slot[1] = atomicAdd(p.tickets + bh, 1u);
+            named_bar_sync(1, 256);
+            if (tmem_slot[1] == gridDim.x - 1) {
+                __threadfence();
+                __nv_bfloat16* dst = (wg == 0 ? p.dv : p.dk) + head_off;
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) {
+                    const int idx = i * 128 + tid128;
+                    if ((idx >> 4) < p.Sk) {
+                        const float4 a = __ldcg(reinterpret_cast<const float4*>(facc) + idx);
+                        *reinterpret_cast<uint2*>(dst + idx * 4) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
                     }
                 }
             }
@@ -1786,7 +1852,9 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
     B2D_BIND(q);
     if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) return set_error(B2D_ERR_SHAPE, "attn_bwd: bad dims");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    {
+    static const bool cross_general = []() { const char* e = getenv("B2D_ATTN_CROSS"); return e && e[0] == 'g'; }();
+    const bool cross = Sk <= TILE && !cross_general;
+    if (!cross) {
         long long total = (long long)B * Sq * H * 8;
         attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
             (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, lse, delta_ws, delta_ws + (long long)B * H * Sq, B, H, Sq);
@@ -1803,13 +1871,12 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
     if ((rc = make_head_map(&mKy, k, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64, TY))) return rc;
     if ((rc = make_head_map(&mVy, v, B, H, Sk, (long long)Sk * 64, 64, (long long)H * Sk * 64, TY))) return rc;
     if ((rc = make_head_map(&mdOy, dout, B, H, Sq, 64, (long long)H * 64, (long long)Sq * H * 64, TY))) return rc;
-    static const bool cross_general = []() { const char* e = getenv("B2D_ATTN_CROSS"); return e && e[0] == 'g'; }();
-    if (Sk <= TILE && !cross_general) {
-        // single key tile (cross attention): one fused pass for dQ, dK, dV
+    if (cross) {
+        // single key tile (cross attention): one fused pass for delta, dQ, dK, dV
         AttnXParams x;
         memset(&x, 0, sizeof(x));
         x.tmQ = mQ; x.tmK = mK; x.tmV = mV; x.tmdO = mdO;
-        x.key_bias = key_bias; x.lse = const_cast<float*>(lse); x.delta = delta_ws;
+        x.key_bias = key_bias; x.lse = const_cast<float*>(lse); x.o = (const __nv_bfloat16*)out;
         x.out = (__nv_bfloat16*)dq; x.dk = (__nv_bfloat16*)dk; x.dv = (__nv_bfloat16*)dv;
         x.B = B; x.H = H; x.Sq = Sq; x.Sk = Sk; x.scale = scale; x.scale_log2 = scale * LOG2E;
         const int n_qt = (Sq + TILE - 1) / TILE;
@@ -1820,17 +1887,13 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
         if (gx > 1) {
             x.acc_dv = delta_ws + 2LL * B * H * Sq;
             x.acc_dk = x.acc_dv + n_kv;
-            cudaError_t e = cudaMemsetAsync(x.acc_dv, 0, 2 * n_kv * sizeof(float), st);
+            x.tickets = reinterpret_cast<unsigned int*>(x.acc_dk + n_kv);
+            cudaError_t e = cudaMemsetAsync(x.acc_dv, 0, (2 * n_kv + (long long)B * H) * sizeof(float), st);
             if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "attn_bwd memset: %s", cudaGetErrorString(e));
         }
         if ((rc = set_smem((const void*)attn_xbwd_kernel, XB_SMEM, "attn_xbwd"))) return rc;
         attn_xbwd_kernel<<<dim3(gx, B * H), X_THREADS, XB_SMEM, st>>>(x);
         B2D_CHECK_LAUNCH("attn_xbwd");
-        if (gx > 1) {
-            f32_to_bf16_kernel<<<(unsigned)((n_kv / 4 + 255) / 256), 256, 0, st>>>(x.acc_dv, (__nv_bfloat16*)dv, n_kv);
-            f32_to_bf16_kernel<<<(unsigned)((n_kv / 4 + 255) / 256), 256, 0, st>>>(x.acc_dk, (__nv_bfloat16*)dk, n_kv);
-            B2D_CHECK_LAUNCH("attn_xbwd(convert)");
-        }
         return 0;
     }
     AttnBwdParams p;

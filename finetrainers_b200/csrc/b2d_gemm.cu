@@ -272,9 +272,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
                     if (epi == B2D_EPI_F32_ATOMIC) {
                         float* o = reinterpret_cast<float*>(p.out) + cbase + (long long)row * p.ldc + col0;
+                        // one thread owns a row, so a warp-wide scalar atomic touches 32 lines: use 16-byte vector atomics
+                        // (4x fewer L2 transactions) whenever the row segment is 16-byte aligned
+                        const bool vec_ok = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.N) atomicAdd(o + j, v[j]);
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            if (vec_ok && col0 + j4 * 4 + 3 < p.N) {
+                                atomicAdd(reinterpret_cast<float4*>(o + j4 * 4),
+                                          make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]));
+                            } else {
+#pragma unroll
+                                for (int j = j4 * 4; j < j4 * 4 + 4; ++j)
+                                    if (col0 + j < p.N) atomicAdd(o + j, v[j]);
+                            }
+                        }
                     } else if (epi == B2D_EPI_F32_ATOMIC_T) {
                         float* o = reinterpret_cast<float*>(p.out) + cbase + row;
 #pragma unroll

@@ -166,7 +166,7 @@ def attn_fwd(q, k, v, key_bias, out, lse, B, H, Sq, Sk, scale):
 
 def attn_bwd_ws_floats(B, H, Sq, Sk):
     """fp32 elements b2d_attn_bwd needs in delta_ws (include/b2d.h)."""
-    return 2 * B * H * Sq + (2 * B * H * Sk * 64 if Sk <= 512 else 0)
+    return 2 * B * H * Sq + (2 * B * H * Sk * 64 + B * H if Sk <= 512 else 0)
 
 
 def attn_bwd(q, k, v, key_bias, out, dout, lse, delta_ws, dq, dk, dv, B, H, Sq, Sk, scale):
@@ -177,10 +177,7 @@ def attn_bwd(q, k, v, key_bias, out, dout, lse, delta_ws, dq, dk, dv, B, H, Sq, 
                                      _ptr(delta_ws), _ptr(dq), _ptr(dk), _ptr(dv), B, H, Sq, Sk, C.c_float(scale),
                                      _stream()), "attn_bwd")
     if Sk <= 128:
-        # single key tile: delta + ONE fused dQ/dK/dV kernel, plus two fp32->bf16 converts when a head's query range is
-        # spread over several CTAs
-        n_qt = (Sq + 127) // 128
-        _count(4 if min(n_qt, max(1, 148 // (B * H))) > 1 else 2)
+        _count(1)  # single key tile: ONE fused delta/dQ/dK/dV kernel
     else:
         # delta + dK/dV + dQ, plus two fp32->bf16 converts when the few-key-tiles split path runs
         split = (B * H * ((Sk + 127) // 128) < 96) and Sk <= 512 and ((Sq + 63) // 64) >= 8

@@ -133,7 +133,8 @@ int b2d_rope_table(float* cos, float* sin, int32_t F, int32_t H, int32_t W, int3
 int b2d_attn_fwd(const void* q, const void* k, const void* v, const float* key_bias, void* out, float* lse, int32_t B,
                  int32_t H, int32_t Sq, int32_t Sk, float scale, void* stream);
 /* dout [B,Sq,H*64] bf16; out as produced by fwd; dq,dk,dv [B,H,S,64] bf16; workspace delta_ws:
- * 2*B*H*Sq floats, plus 2*B*H*Sk*64 floats when Sk <= 512 (fp32 dK/dV accumulators of the split cross-attention path). */
+ * 2*B*H*Sq floats, plus 2*B*H*Sk*64 + B*H floats when Sk <= 512 (fp32 dK/dV accumulators and per-head arrival
+ * counters of the cross-attention paths; the library zeroes what it uses, the caller only provides the space). */
 int b2d_attn_bwd(const void* q, const void* k, const void* v, const float* key_bias, const void* out, const void* dout,
                  const float* lse, float* delta_ws, void* dq, void* dk, void* dv, int32_t B, int32_t H, int32_t Sq,
                  int32_t Sk, float scale, void* stream);

@@ -356,12 +356,23 @@ def check_attn():
         try:
             for _ in range(3):
                 fn()
+            # these launches are short enough to be host-bound from Python: time a CUDA-graph replay of 20 calls
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                fn()
+                side.synchronize()
+                with torch.cuda.graph(gr, stream=side):
+                    for _ in range(20):
+                        fn()
+            gr.replay(); torch.cuda.synchronize()
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(20):
-                fn()
+            for _ in range(5):
+                gr.replay()
             e1.record(); torch.cuda.synchronize()
-            print(f"[time] {name} Sq=2688 Sk=128 H=32: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us", flush=True)
+            print(f"[time] {name} Sq=2688 Sk=128 H=32: {e0.elapsed_time(e1) / 100 * 1e3:.1f} us (graph replay)", flush=True)
         except Exception as e:
             print("EXC timing", name, e)
     qt = q.clone().requires_grad_(True)
