@@ -1611,20 +1611,28 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_co
             }
         };
 
+        // delta = sum_d O[q,d] dO[q,d]: the O row comes straight from global, the dO row from the tile the TMA already
+        // staged (s_full implies it has landed; it stays until the tile's last MMA).  The per-row global operands (O row,
+        // lse) of tile t+1 are fetched while tile t is processed, so their DRAM latency never sits on the tile chain.
+        uint4 o_nxt[8];
+        float lse_nxt;
+        auto fetch_row = [&](int tt) {
+            const int qr = min((t0 + tt) * TILE + r, p.Sq - 1);
+            const uint4* og = reinterpret_cast<const uint4*>(p.o + ((long long)b * p.Sq + qr) * (p.H * HD) + h * HD);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) o_nxt[u] = __ldg(og + u);
+            lse_nxt = __ldg(p.lse + bhoff * p.Sq + qr);
+        };
+        fetch_row(0);
         for (int t = 0; t < n; ++t) {
             const int j = t & 1;
             const int qrow = (t0 + t) * TILE + r;
             const bool row_ok = qrow < p.Sq;
-            const float rowA = row_ok ? -p.lse[bhoff * p.Sq + qrow] * LOG2E : -INFINITY;
-            // delta = sum_d O[q,d] dO[q,d]: the O row comes straight from global (issued before the wait below), the dO
-            // row from the tile the TMA already staged (s_full implies it has landed; it stays until the tile's last MMA)
+            const float rowA = row_ok ? -lse_nxt * LOG2E : -INFINITY;
             uint4 o4[8];
-            {
-                const uint4* og = reinterpret_cast<const uint4*>(
-                    p.o + ((long long)b * p.Sq + (row_ok ? qrow : 0)) * (p.H * HD) + h * HD);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) o4[u] = __ldg(og + u);
-            }
+            for (int u = 0; u < 8; ++u) o4[u] = o_nxt[u];
+            if (t + 1 < n) fetch_row(t + 1);
             uint8_t* myP = sP + j * 2 * X_PS_BYTES + wg * X_CHUNK;
             uint8_t* myDS = myP + X_PS_BYTES;
             mbar_wait(s_full, (uint32_t)(t & 1));
