@@ -44,6 +44,9 @@ __device__ __forceinline__ float2 block_sum2(float a, float b) {
 // ------------------------------------------------------------------------------------------------
 // norm + modulate
 // ------------------------------------------------------------------------------------------------
+// Every global operand of a row is requested BEFORE the first block reduction: a row's critical path is then one memory
+// round trip + the reductions instead of two or three dependent round trips (these kernels have ~16 KB in flight per
+// CTA and 8 CTAs per SM, so the dependent-latency chain, not bandwidth, was what bounded them).
 template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_fwd_kernel(
     const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ shift_tab,
@@ -53,13 +56,25 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_fwd_kernel(
     const int row = blockIdx.x;
     const int b = row / rows_per_sample;
     const __nv_bfloat16* xr = x + (long long)row * D;
+    uint4 xq[NCH], q_sht[NCH], q_she[NCH], q_sct[NCH], q_sce[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            xq[c] = ldg16(xr + col);
+            q_sht[c] = ldg16(shift_tab + col);
+            q_she[c] = ldg16(shift_emb + (long long)b * emb_stride + col);
+            q_sct[c] = ldg16(scale_tab + col);
+            q_sce[c] = ldg16(scale_emb + (long long)b * emb_stride + col);
+        }
+    }
     float v[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
-            unpack8(ldg16(xr + col), v[c]);
+            unpack8(xq[c], v[c]);
 #pragma unroll
             for (int e = 0; e < 8; ++e) { s1 += v[c][e]; s2 += v[c][e] * v[c][e]; }
         }
@@ -87,12 +102,12 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_fwd_kernel(
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
             float sh[8], sc[8], t[8];
-            unpack8(ldg16(shift_tab + col), sh);
-            unpack8(ldg16(shift_emb + (long long)b * emb_stride + col), t);
+            unpack8(q_sht[c], sh);
+            unpack8(q_she[c], t);
 #pragma unroll
             for (int e = 0; e < 8; ++e) sh[e] += t[e];
-            unpack8(ldg16(scale_tab + col), sc);
-            unpack8(ldg16(scale_emb + (long long)b * emb_stride + col), t);
+            unpack8(q_sct[c], sc);
+            unpack8(q_sce[c], t);
 #pragma unroll
             for (int e = 0; e < 8; ++e) sc[e] += t[e];
             float o[8];
@@ -113,13 +128,29 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
     const int row = blockIdx.x;
     const int b = row / rows_per_sample;
     const long long ro = (long long)row * D;
+    uint4 q_x[NCH], q_dy[NCH], q_sct[NCH], q_sce[NCH], q_in[NCH], q_gt[NCH], q_ge[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            q_x[c] = ldg16(x + ro + col);
+            q_dy[c] = ldg16(dy + ro + col);
+            q_sct[c] = ldg16(scale_tab + col);
+            q_sce[c] = ldg16(scale_emb + (long long)b * emb_stride + col);
+            q_in[c] = dx_in != nullptr ? ldg16(dx_in + ro + col) : make_uint4(0, 0, 0, 0);
+            if (out2 != nullptr) {
+                q_gt[c] = ldg16(gate2_tab + col);
+                q_ge[c] = ldg16(gate2_emb + (long long)b * emb_stride + col);
+            }
+        }
+    }
     float xv[NCH][8], g[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
-            unpack8(ldg16(x + ro + col), xv[c]);
+            unpack8(q_x[c], xv[c]);
 #pragma unroll
             for (int e = 0; e < 8; ++e) { s1 += xv[c][e]; s2 += xv[c][e] * xv[c][e]; }
         }
@@ -148,9 +179,9 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
             float sc[8], t[8], d[8];
-            unpack8(ldg16(scale_tab + col), sc);
-            unpack8(ldg16(scale_emb + (long long)b * emb_stride + col), t);
-            unpack8(ldg16(dy + ro + col), d);
+            unpack8(q_sct[c], sc);
+            unpack8(q_sce[c], t);
+            unpack8(q_dy[c], d);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 g[c][e] = d[e] * (1.f + sc[e] + t[e]);
@@ -168,11 +199,7 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
             float o[8];
-            if (dx_in != nullptr) unpack8(ldg16(dx_in + ro + col), o);
-            else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = 0.f;
-            }
+            unpack8(q_in[c], o);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] += rstd * (g[c][e] - mg - xv[c][e] * mgx);
             uint4 packed = pack8(o);
@@ -180,8 +207,8 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
             if (out2 != nullptr) {
                 float r[8], gt[8], ge[8];
                 unpack8(packed, r);  // the rounded value is what downstream sees
-                unpack8(ldg16(gate2_tab + col), gt);
-                unpack8(ldg16(gate2_emb + (long long)b * emb_stride + col), ge);
+                unpack8(q_gt[c], gt);
+                unpack8(q_ge[c], ge);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) r[e] *= (gt[e] + ge[e]);
                 stg16(out2 + ro + col, pack8(r));
@@ -209,137 +236,232 @@ __global__ void colscale_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
 }
 
 // ------------------------------------------------------------------------------------------------
-// q/k RMSNorm (affine, across all heads) + RoPE + head split:  src[row, col_off + c] -> dst[b, h, s, d]
+// q/k RMSNorm (affine, across all heads) + RoPE + head split for up to three column segments of one packed row
+// (q | k | v of the fused QKV projection, or k | v of cross attention):  src[row, col_off + i*D + c] -> dst_i[b, h, s, d].
+// One CTA handles all segments of its row: the (cos, sin) row is read once for q AND k, every global operand is
+// requested before the first reduction, and the two RMS statistics share one block reduction.
 // ------------------------------------------------------------------------------------------------
+struct QkvSegArgs {
+    const __nv_bfloat16* w[3];   // RMSNorm weight of segment i, or null: no norm
+    __nv_bfloat16* dst[3];       // fwd: head-split outputs;  bwd: head-split upstream gradients (read)
+    int nseg;
+    int rope_mask;               // bit i: segment i is rotated
+};
+
 template <int NCH>
-__global__ void __launch_bounds__(ROW_THREADS) qknorm_rope_fwd_kernel(
-    const __nv_bfloat16* __restrict__ src, long long ld, long long col_off, const __nv_bfloat16* __restrict__ weight,
-    const float* __restrict__ cosT, const float* __restrict__ sinT, __nv_bfloat16* __restrict__ dst, int S, int H,
-    int norm, float eps) {
+__global__ void __launch_bounds__(ROW_THREADS) qkv_norm_rope_fwd_kernel(
+    const __nv_bfloat16* __restrict__ src, long long ld, long long col_off, const QkvSegArgs a,
+    const float* __restrict__ cosT, const float* __restrict__ sinT, int S, int H, float eps) {
     const int D = H * 64;
     const int row = blockIdx.x;
     const int b = row / S, s = row % S;
     const __nv_bfloat16* xr = src + (long long)row * ld + col_off;
-    float v[NCH][8];
-    float s2 = 0.f;
+    uint4 xq[3][NCH], wq[3][NCH];
+    float4 c4[NCH], s4[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
-            unpack8(ldg16(xr + col), v[c]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) s2 += v[c][e] * v[c][e];
+            for (int i = 0; i < 3; ++i) {
+                if (i < a.nseg) {
+                    xq[i][c] = ldg16(xr + (long long)i * D + col);
+                    if (a.w[i] != nullptr) wq[i][c] = ldg16(a.w[i] + col);
+                }
+            }
+            if (a.rope_mask) {
+                // tables hold one (cos, sin) per rotary PAIR: [S, D/2] fp32 (the reference's repeat_interleave(2) is implicit)
+                c4[c] = *reinterpret_cast<const float4*>(cosT + ((long long)s * D + col) / 2);
+                s4[c] = *reinterpret_cast<const float4*>(sinT + ((long long)s * D + col) / 2);
+            }
         }
     }
-    float rstd = 1.f;
-    if (norm) rstd = rsqrtf(block_sum2(s2, 0.f).x / D + eps);
+    float ss[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
-        if (col < D) {
-            float n[8];
-            if (norm) {
-                float w[8];
-                unpack8(ldg16(weight + col), w);
+    for (int i = 0; i < 3; ++i) {
+        if (i < a.nseg && a.w[i] != nullptr) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) n[e] = v[c][e] * rstd * w[e];
-            } else {
+            for (int c = 0; c < NCH; ++c) {
+                const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+                if (col < D) {
+                    float v[8];
+                    unpack8(xq[i][c], v);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) n[e] = v[c][e];
-            }
-            float o[8];
-            if (cosT != nullptr) {
-                // tables hold one (cos, sin) per rotary PAIR: [S, D/2] fp32 (the reference's repeat_interleave(2) is implicit)
-                const float4 c4 = *reinterpret_cast<const float4*>(cosT + ((long long)s * D + col) / 2);
-                const float4 s4 = *reinterpret_cast<const float4*>(sinT + ((long long)s * D + col) / 2);
-                const float cs[4] = {c4.x, c4.y, c4.z, c4.w};
-                const float sn[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                    o[e] = n[e] * cs[e >> 1] - n[e + 1] * sn[e >> 1];
-                    o[e + 1] = n[e + 1] * cs[e >> 1] + n[e] * sn[e >> 1];
+                    for (int e = 0; e < 8; ++e) ss[i] += v[e] * v[e];
                 }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = n[e];
             }
-            const int h = col >> 6, d = col & 63;
-            stg16(dst + (((long long)b * H + h) * S + s) * 64 + d, pack8(o));
+        }
+    }
+    float rstd[3] = {1.f, 1.f, 1.f};
+    if (a.w[0] != nullptr || (a.nseg > 1 && a.w[1] != nullptr)) {
+        const float2 t = block_sum2(ss[0], ss[1]);
+        rstd[0] = rsqrtf(t.x / D + eps);
+        rstd[1] = rsqrtf(t.y / D + eps);
+    }
+    if (a.nseg > 2 && a.w[2] != nullptr) rstd[2] = rsqrtf(block_sum2(ss[2], 0.f).x / D + eps);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (i < a.nseg) {
+            const bool norm = a.w[i] != nullptr;
+            const bool rope = (a.rope_mask >> i) & 1;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+                if (col < D) {
+                    float n[8];
+                    unpack8(xq[i][c], n);
+                    if (norm) {
+                        float w[8];
+                        unpack8(wq[i][c], w);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) n[e] = n[e] * rstd[i] * w[e];
+                    }
+                    float o[8];
+                    if (rope) {
+                        const float cs[4] = {c4[c].x, c4[c].y, c4[c].z, c4[c].w};
+                        const float sn[4] = {s4[c].x, s4[c].y, s4[c].z, s4[c].w};
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2) {
+                            o[e] = n[e] * cs[e >> 1] - n[e + 1] * sn[e >> 1];
+                            o[e + 1] = n[e + 1] * cs[e >> 1] + n[e] * sn[e >> 1];
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = n[e];
+                    }
+                    const int h = col >> 6, d = col & 63;
+                    stg16(a.dst[i] + (((long long)b * H + h) * S + s) * 64 + d, pack8(o));
+                }
+            }
         }
     }
 }
 
 template <int NCH>
-__global__ void __launch_bounds__(ROW_THREADS) qknorm_rope_bwd_kernel(
-    const __nv_bfloat16* __restrict__ dyh, const __nv_bfloat16* __restrict__ x, long long ld, long long col_off,
-    const __nv_bfloat16* __restrict__ weight, const float* __restrict__ cosT, const float* __restrict__ sinT,
-    __nv_bfloat16* __restrict__ dx, long long ld_dx, long long dx_col_off, int S, int H, int norm, float eps) {
+__global__ void __launch_bounds__(ROW_THREADS) qkv_norm_rope_bwd_kernel(
+    const __nv_bfloat16* __restrict__ x, long long ld, long long col_off, const QkvSegArgs a,
+    const float* __restrict__ cosT, const float* __restrict__ sinT, __nv_bfloat16* __restrict__ dx, long long ld_dx,
+    long long dx_col_off, int S, int H, float eps) {
     const int D = H * 64;
     const int row = blockIdx.x;
     const int b = row / S, s = row % S;
-    float xv[NCH][8], g[NCH][8];
-    float s2 = 0.f;
-    if (norm) {
-        const __nv_bfloat16* xr = x + (long long)row * ld + col_off;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const int col = (c * ROW_THREADS + threadIdx.x) * 8;
-            if (col < D) {
-                unpack8(ldg16(xr + col), xv[c]);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) s2 += xv[c][e] * xv[c][e];
-            }
-        }
-    }
-    float rstd = 1.f;
-    if (norm) rstd = rsqrtf(block_sum2(s2, 0.f).x / D + eps);
-    float sgx = 0.f;
+    const __nv_bfloat16* xr = x + (long long)row * ld + col_off;
+    uint4 xq[3][NCH], wq[3][NCH], dq[3][NCH];
+    float4 c4[NCH], s4[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
             const int h = col >> 6, d = col & 63;
-            float dy[8], dn[8];
-            unpack8(ldg16(dyh + (((long long)b * H + h) * S + s) * 64 + d), dy);
-            if (cosT != nullptr) {
-                const float4 c4 = *reinterpret_cast<const float4*>(cosT + ((long long)s * D + col) / 2);
-                const float4 s4 = *reinterpret_cast<const float4*>(sinT + ((long long)s * D + col) / 2);
-                const float cs[4] = {c4.x, c4.y, c4.z, c4.w};
-                const float sn[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                    dn[e] = dy[e] * cs[e >> 1] + dy[e + 1] * sn[e >> 1];
-                    dn[e + 1] = dy[e + 1] * cs[e >> 1] - dy[e] * sn[e >> 1];
+            for (int i = 0; i < 3; ++i) {
+                if (i < a.nseg) {
+                    dq[i][c] = ldg16(a.dst[i] + (((long long)b * H + h) * S + s) * 64 + d);
+                    if (a.w[i] != nullptr) {
+                        xq[i][c] = ldg16(xr + (long long)i * D + col);
+                        wq[i][c] = ldg16(a.w[i] + col);
+                    }
                 }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) dn[e] = dy[e];
             }
-            if (norm) {
-                float w[8];
-                unpack8(ldg16(weight + col), w);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    g[c][e] = dn[e] * w[e];
-                    xv[c][e] *= rstd;
-                    sgx += g[c][e] * xv[c][e];
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) g[c][e] = dn[e];
+            if (a.rope_mask) {
+                c4[c] = *reinterpret_cast<const float4*>(cosT + ((long long)s * D + col) / 2);
+                s4[c] = *reinterpret_cast<const float4*>(sinT + ((long long)s * D + col) / 2);
             }
         }
     }
-    float mgx = 0.f;
-    if (norm) mgx = block_sum2(sgx, 0.f).x / D;
+    float ss[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
-        if (col < D) {
-            float o[8];
+    for (int i = 0; i < 3; ++i) {
+        if (i < a.nseg && a.w[i] != nullptr) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = norm ? rstd * (g[c][e] - xv[c][e] * mgx) : g[c][e];
-            stg16(dx + (long long)row * ld_dx + dx_col_off + col, pack8(o));
+            for (int c = 0; c < NCH; ++c) {
+                const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+                if (col < D) {
+                    float v[8];
+                    unpack8(xq[i][c], v);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) ss[i] += v[e] * v[e];
+                }
+            }
+        }
+    }
+    float rstd[3] = {1.f, 1.f, 1.f};
+    const bool n01 = a.w[0] != nullptr || (a.nseg > 1 && a.w[1] != nullptr);
+    const bool n2 = a.nseg > 2 && a.w[2] != nullptr;
+    if (n01) {
+        const float2 t = block_sum2(ss[0], ss[1]);
+        rstd[0] = rsqrtf(t.x / D + eps);
+        rstd[1] = rsqrtf(t.y / D + eps);
+    }
+    if (n2) rstd[2] = rsqrtf(block_sum2(ss[2], 0.f).x / D + eps);
+    // g = rope^T(dy) * w ; xhat = x * rstd ; dx = rstd * (g - xhat * mean(g * xhat))
+    float g[3][NCH][8];
+    float sgx[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (i < a.nseg) {
+            const bool norm = a.w[i] != nullptr;
+            const bool rope = (a.rope_mask >> i) & 1;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+                if (col < D) {
+                    float dy[8];
+                    unpack8(dq[i][c], dy);
+                    if (rope) {
+                        const float cs[4] = {c4[c].x, c4[c].y, c4[c].z, c4[c].w};
+                        const float sn[4] = {s4[c].x, s4[c].y, s4[c].z, s4[c].w};
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2) {
+                            g[i][c][e] = dy[e] * cs[e >> 1] + dy[e + 1] * sn[e >> 1];
+                            g[i][c][e + 1] = dy[e + 1] * cs[e >> 1] - dy[e] * sn[e >> 1];
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) g[i][c][e] = dy[e];
+                    }
+                    if (norm) {
+                        float w[8], xv[8];
+                        unpack8(wq[i][c], w);
+                        unpack8(xq[i][c], xv);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            g[i][c][e] *= w[e];
+                            sgx[i] += g[i][c][e] * (xv[e] * rstd[i]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    float mgx[3] = {0.f, 0.f, 0.f};
+    if (n01) {
+        const float2 t = block_sum2(sgx[0], sgx[1]);
+        mgx[0] = t.x / D;
+        mgx[1] = t.y / D;
+    }
+    if (n2) mgx[2] = block_sum2(sgx[2], 0.f).x / D;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (i < a.nseg) {
+            const bool norm = a.w[i] != nullptr;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+                if (col < D) {
+                    float o[8];
+                    if (norm) {
+                        float xv[8];
+                        unpack8(xq[i][c], xv);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = rstd[i] * (g[i][c][e] - (xv[e] * rstd[i]) * mgx[i]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = g[i][c][e];
+                    }
+                    stg16(dx + (long long)row * ld_dx + dx_col_off + (long long)i * D + col, pack8(o));
+                }
+            }
         }
     }
 }
@@ -560,17 +682,43 @@ extern "C" int b2d_colscale(const void* x, void* out, const void* tab, const voi
     return 0;
 }
 
+static int launch_qkv_fwd(const void* src, int64_t ld, int64_t col_off, const QkvSegArgs& a, const void* cos,
+                          const void* sin, int B, int S, int H, float eps, void* stream) {
+    if (int rc = check_rowop(B * S, H * 64, S)) return rc;
+    if ((ld % 8) || (col_off % 8)) return set_error(B2D_ERR_ALIGN, "qkv_norm_rope: ld/col_off must be multiples of 8");
+    if (a.nseg < 1 || a.nseg > 3) return set_error(B2D_ERR_SHAPE, "qkv_norm_rope: 1..3 segments");
+    if (a.rope_mask && (cos == nullptr || sin == nullptr)) return set_error(B2D_ERR_SHAPE, "qkv_norm_rope: rope needs tables");
+    ROW_DISPATCH(H * 64, qkv_norm_rope_fwd_kernel, B * S, (const __nv_bfloat16*)src, ld, col_off, a, (const float*)cos,
+                 (const float*)sin, S, H, eps);
+    B2D_CHECK_LAUNCH("qkv_norm_rope_fwd");
+    return 0;
+}
+
+static int launch_qkv_bwd(const void* x, int64_t ld, int64_t col_off, const QkvSegArgs& a, const void* cos,
+                          const void* sin, void* dx, int64_t ld_dx, int64_t dx_col_off, int B, int S, int H, float eps,
+                          void* stream) {
+    if (int rc = check_rowop(B * S, H * 64, S)) return rc;
+    if ((ld % 8) || (col_off % 8) || (ld_dx % 8) || (dx_col_off % 8))
+        return set_error(B2D_ERR_ALIGN, "qkv_norm_rope_bwd: ld/col_off must be multiples of 8");
+    if (a.nseg < 1 || a.nseg > 3) return set_error(B2D_ERR_SHAPE, "qkv_norm_rope_bwd: 1..3 segments");
+    if (a.rope_mask && (cos == nullptr || sin == nullptr)) return set_error(B2D_ERR_SHAPE, "qkv_norm_rope_bwd: rope needs tables");
+    ROW_DISPATCH(H * 64, qkv_norm_rope_bwd_kernel, B * S, (const __nv_bfloat16*)x, ld, col_off, a, (const float*)cos,
+                 (const float*)sin, (__nv_bfloat16*)dx, ld_dx, dx_col_off, S, H, eps);
+    B2D_CHECK_LAUNCH("qkv_norm_rope_bwd");
+    return 0;
+}
+
 extern "C" int b2d_qknorm_rope_fwd(const void* src, int64_t ld, int64_t col_off, const void* weight, const void* cos,
                                    const void* sin, void* dst, int32_t B, int32_t S, int32_t H, int32_t norm,
                                    float eps, void* stream) {
     B2D_BIND(src);
-    if (int rc = check_rowop(B * S, H * 64, S)) return rc;
-    if ((ld % 8) || (col_off % 8)) return set_error(B2D_ERR_ALIGN, "qknorm_rope: ld/col_off must be multiples of 8");
-    ROW_DISPATCH(H * 64, qknorm_rope_fwd_kernel, B * S, (const __nv_bfloat16*)src, ld, col_off,
-                                                              (const __nv_bfloat16*)weight, (const float*)cos,
-                                                              (const float*)sin, (__nv_bfloat16*)dst, S, H, norm, eps);
-    B2D_CHECK_LAUNCH("qknorm_rope_fwd");
-    return 0;
+    QkvSegArgs a = {};
+    a.nseg = 1;
+    a.w[0] = norm ? (const __nv_bfloat16*)weight : nullptr;
+    if (norm && weight == nullptr) return set_error(B2D_ERR_SHAPE, "qknorm_rope: norm needs a weight");
+    a.dst[0] = (__nv_bfloat16*)dst;
+    a.rope_mask = cos != nullptr ? 1 : 0;
+    return launch_qkv_fwd(src, ld, col_off, a, cos, sin, B, S, H, eps, stream);
 }
 
 extern "C" int b2d_qknorm_rope_bwd(const void* dsrc_heads, const void* x, int64_t ld, int64_t col_off,
@@ -578,14 +726,41 @@ extern "C" int b2d_qknorm_rope_bwd(const void* dsrc_heads, const void* x, int64_
                                    int64_t dx_col_off, int32_t B, int32_t S, int32_t H, int32_t norm, float eps,
                                    void* stream) {
     B2D_BIND(dsrc_heads);
-    if (int rc = check_rowop(B * S, H * 64, S)) return rc;
-    if ((ld % 8) || (col_off % 8) || (ld_dx % 8) || (dx_col_off % 8))
-        return set_error(B2D_ERR_ALIGN, "qknorm_rope_bwd: ld/col_off must be multiples of 8");
-    ROW_DISPATCH(H * 64, qknorm_rope_bwd_kernel, B * S,
-        (const __nv_bfloat16*)dsrc_heads, (const __nv_bfloat16*)x, ld, col_off, (const __nv_bfloat16*)weight,
-        (const float*)cos, (const float*)sin, (__nv_bfloat16*)dx, ld_dx, dx_col_off, S, H, norm, eps);
-    B2D_CHECK_LAUNCH("qknorm_rope_bwd");
-    return 0;
+    QkvSegArgs a = {};
+    a.nseg = 1;
+    a.w[0] = norm ? (const __nv_bfloat16*)weight : nullptr;
+    if (norm && weight == nullptr) return set_error(B2D_ERR_SHAPE, "qknorm_rope_bwd: norm needs a weight");
+    a.dst[0] = (__nv_bfloat16*)const_cast<void*>(dsrc_heads);
+    a.rope_mask = cos != nullptr ? 1 : 0;
+    return launch_qkv_bwd(x, ld, col_off, a, cos, sin, dx, ld_dx, dx_col_off, B, S, H, eps, stream);
+}
+
+extern "C" int b2d_qkv_norm_rope_fwd(const void* src, int64_t ld, int64_t col_off, int32_t nseg, const void* w0,
+                                     const void* w1, const void* w2, int32_t rope_mask, const void* cos, const void* sin,
+                                     void* dst0, void* dst1, void* dst2, int32_t B, int32_t S, int32_t H, float eps,
+                                     void* stream) {
+    B2D_BIND(src);
+    QkvSegArgs a = {};
+    a.nseg = nseg;
+    a.w[0] = (const __nv_bfloat16*)w0; a.w[1] = (const __nv_bfloat16*)w1; a.w[2] = (const __nv_bfloat16*)w2;
+    a.dst[0] = (__nv_bfloat16*)dst0; a.dst[1] = (__nv_bfloat16*)dst1; a.dst[2] = (__nv_bfloat16*)dst2;
+    a.rope_mask = rope_mask;
+    return launch_qkv_fwd(src, ld, col_off, a, cos, sin, B, S, H, eps, stream);
+}
+
+extern "C" int b2d_qkv_norm_rope_bwd(const void* dy0, const void* dy1, const void* dy2, const void* x, int64_t ld,
+                                     int64_t col_off, int32_t nseg, const void* w0, const void* w1, const void* w2,
+                                     int32_t rope_mask, const void* cos, const void* sin, void* dx, int64_t ld_dx,
+                                     int64_t dx_col_off, int32_t B, int32_t S, int32_t H, float eps, void* stream) {
+    B2D_BIND(dy0);
+    QkvSegArgs a = {};
+    a.nseg = nseg;
+    a.w[0] = (const __nv_bfloat16*)w0; a.w[1] = (const __nv_bfloat16*)w1; a.w[2] = (const __nv_bfloat16*)w2;
+    a.dst[0] = (__nv_bfloat16*)const_cast<void*>(dy0);
+    a.dst[1] = (__nv_bfloat16*)const_cast<void*>(dy1);
+    a.dst[2] = (__nv_bfloat16*)const_cast<void*>(dy2);
+    a.rope_mask = rope_mask;
+    return launch_qkv_bwd(x, ld, col_off, a, cos, sin, dx, ld_dx, dx_col_off, B, S, H, eps, stream);
 }
 
 extern "C" int b2d_rope_table(float* cos, float* sin, int32_t F, int32_t H, int32_t W, int32_t D, float sf, float sh,

@@ -88,7 +88,7 @@ def check(rc: int, what: str = ""):
 EXPORTS = [
     "b2d_version", "b2d_last_error", "b2d_device_check", "b2d_gemm",
     "b2d_norm_modulate_fwd", "b2d_norm_modulate_bwd", "b2d_colscale",
-    "b2d_qknorm_rope_fwd", "b2d_qknorm_rope_bwd", "b2d_rope_table",
+    "b2d_qknorm_rope_fwd", "b2d_qknorm_rope_bwd", "b2d_qkv_norm_rope_fwd", "b2d_qkv_norm_rope_bwd", "b2d_rope_table",
     "b2d_attn_fwd", "b2d_attn_bwd",
     "b2d_prep_noise_pack", "b2d_loss_mse", "b2d_timestep_sinusoid", "b2d_cast_f32_bf16",
     "b2d_sumsq", "b2d_adamw_clip",

@@ -483,9 +483,8 @@ class B200LTXTransformer(nn.Module):
             self._lin(n1, e["Wqkv"], e["bqkv"], ws["qkv"][l], R, 3 * d, d,
                       lora=(e["Ab_qkv"], e["Bb_qkv"], ws["u_qkv"][l], 3) if rp else None)
             # K7: q/k RMSNorm + RoPE + head split
-            ops.qknorm_rope_fwd(ws["qkv"][l], 3 * d, 0, e["nq1"], cos, sin, ws["qh"][l], B, S, H, True, cfg.qk_norm_eps)
-            ops.qknorm_rope_fwd(ws["qkv"][l], 3 * d, d, e["nk1"], cos, sin, ws["kh"][l], B, S, H, True, cfg.qk_norm_eps)
-            ops.qknorm_rope_fwd(ws["qkv"][l], 3 * d, 2 * d, None, None, None, ws["vh"][l], B, S, H, False, cfg.qk_norm_eps)
+            ops.qkv_norm_rope_fwd(ws["qkv"][l], 3 * d, 0, (e["nq1"], e["nk1"], None), 0b011, cos, sin,
+                                  (ws["qh"][l], ws["kh"][l], ws["vh"][l]), B, S, H, cfg.qk_norm_eps)
             # K8: self attention
             ops.attn_fwd(ws["qh"][l], ws["kh"][l], ws["vh"][l], None, ws["ao"][l], ws["lse"][l], B, H, S, S, scale)
             # K9: out proj + gated residual (gate_msa = row 2)
@@ -501,8 +500,8 @@ class B200LTXTransformer(nn.Module):
             self._lin(enc, e["Wkv2"], e["bkv2"], ws["kv2"][l], RL, 2 * d, d,
                       lora=(e["Ab_kv2"], e["Bb_kv2"], ws["u_kv2"][l], 2) if rp else None)
             ops.qknorm_rope_fwd(ws["q2"][l], d, 0, e["nq2"], None, None, ws["q2h"][l], B, S, H, True, cfg.qk_norm_eps)
-            ops.qknorm_rope_fwd(ws["kv2"][l], 2 * d, 0, e["nk2"], None, None, ws["k2h"][l], B, L, H, True, cfg.qk_norm_eps)
-            ops.qknorm_rope_fwd(ws["kv2"][l], 2 * d, d, None, None, None, ws["v2h"][l], B, L, H, False, cfg.qk_norm_eps)
+            ops.qkv_norm_rope_fwd(ws["kv2"][l], 2 * d, 0, (e["nk2"], None), 0, None, None, (ws["k2h"][l], ws["v2h"][l]),
+                                  B, L, H, cfg.qk_norm_eps)
             ops.attn_fwd(ws["q2h"][l], ws["k2h"][l], ws["v2h"][l], key_bias, ws["ao2"][l], ws["lse2"][l], B, H, S, L, scale)
             self._lin(ws["ao2"][l], e["Wo2"], e["bo2"], ws["h2"][l], R, d, d,
                       lora=(e["Ab_o2"], e["Bb_o2"], ws["u_o2"][l], 1) if rp else None,
@@ -617,10 +616,8 @@ class B200LTXTransformer(nn.Module):
                          ws["delta"], ws["dqh"], ws["dk2h"], ws["dv2h"], B, H, S, L, scale)
             ops.qknorm_rope_bwd(ws["dqh"], ws["q2"][l], d, 0, e["nq2"], None, None, dq2, d, 0, B, S, H, True,
                                 cfg.qk_norm_eps)
-            ops.qknorm_rope_bwd(ws["dk2h"], ws["kv2"][l], 2 * d, 0, e["nk2"], None, None, dkv2, 2 * d, 0, B, L, H,
-                                True, cfg.qk_norm_eps)
-            ops.qknorm_rope_bwd(ws["dv2h"], ws["kv2"][l], 2 * d, d, None, None, None, dkv2, 2 * d, d, B, L, H, False,
-                                cfg.qk_norm_eps)
+            ops.qkv_norm_rope_bwd((ws["dk2h"], ws["dv2h"]), ws["kv2"][l], 2 * d, 0, (e["nk2"], None), 0, None, None, dkv2,
+                                  2 * d, 0, B, L, H, cfg.qk_norm_eps)
             du = self._lora_du(dq2, ws["du_q2"][l], e, "q2", R, d, 1)
             # dh1 = dh2 + dq2 W_q2 + du A ; gated copy (gate_msa, row 2) = dy of the self-attention out-proj
             ops.gemm(dq2, e["Wq2"], dh, M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_q2"], K2=rp,
@@ -632,12 +629,8 @@ class B200LTXTransformer(nn.Module):
             ops.gemm(dyo, e["Wo"], ws["da"], M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_o"], K2=rp)
             ops.attn_bwd(ws["qh"][l], ws["kh"][l], ws["vh"][l], None, ws["ao"][l], ws["da"], ws["lse"][l], ws["delta"],
                          ws["dqh"], ws["dkh"], ws["dvh"], B, H, S, S, scale)
-            ops.qknorm_rope_bwd(ws["dqh"], ws["qkv"][l], 3 * d, 0, e["nq1"], cos, sin, dqkv, 3 * d, 0, B, S, H, True,
-                                cfg.qk_norm_eps)
-            ops.qknorm_rope_bwd(ws["dkh"], ws["qkv"][l], 3 * d, d, e["nk1"], cos, sin, dqkv, 3 * d, d, B, S, H, True,
-                                cfg.qk_norm_eps)
-            ops.qknorm_rope_bwd(ws["dvh"], ws["qkv"][l], 3 * d, 2 * d, None, None, None, dqkv, 3 * d, 2 * d, B, S, H,
-                                False, cfg.qk_norm_eps)
+            ops.qkv_norm_rope_bwd((ws["dqh"], ws["dkh"], ws["dvh"]), ws["qkv"][l], 3 * d, 0, (e["nq1"], e["nk1"], None),
+                                  0b011, cos, sin, dqkv, 3 * d, 0, B, S, H, cfg.qk_norm_eps)
             du = self._lora_du(dqkv, ws["du_qkv"][l], e, "qkv", R, 3 * d, 3)
             if l == 0 and self.skip_block0_dx:
                 break  # nothing trainable upstream of block 0's adapters (proj_in / embeds are frozen)

@@ -150,6 +150,31 @@ def qknorm_rope_bwd(dyh, x, ld, col_off, weight, cos, sin, dx, ld_dx, dx_col_off
     return dx
 
 
+def qkv_norm_rope_fwd(src, ld, col_off, weights, rope_mask, cos, sin, dsts, B, S, H, eps):
+    """nseg = len(dsts) consecutive D-wide segments of src rows -> head-split dsts in ONE launch (b2d.h)."""
+    n = len(dsts)
+    w = list(weights) + [None] * (3 - n)
+    d = list(dsts) + [None] * (3 - n)
+    with _Timed("qknorm_rope_fwd"):
+        check(_l.load().b2d_qkv_norm_rope_fwd(_ptr(src), C.c_int64(ld), C.c_int64(col_off), n, _ptr(w[0]), _ptr(w[1]),
+                                              _ptr(w[2]), int(rope_mask), _ptr(cos), _ptr(sin), _ptr(d[0]), _ptr(d[1]),
+                                              _ptr(d[2]), B, S, H, C.c_float(eps), _stream()), "qkv_norm_rope_fwd")
+    _count()
+
+
+def qkv_norm_rope_bwd(dys, x, ld, col_off, weights, rope_mask, cos, sin, dx, ld_dx, dx_col_off, B, S, H, eps):
+    n = len(dys)
+    w = list(weights) + [None] * (3 - n)
+    d = list(dys) + [None] * (3 - n)
+    with _Timed("qknorm_rope_bwd"):
+        check(_l.load().b2d_qkv_norm_rope_bwd(_ptr(d[0]), _ptr(d[1]), _ptr(d[2]), _ptr(x), C.c_int64(ld),
+                                              C.c_int64(col_off), n, _ptr(w[0]), _ptr(w[1]), _ptr(w[2]), int(rope_mask),
+                                              _ptr(cos), _ptr(sin), _ptr(dx), C.c_int64(ld_dx), C.c_int64(dx_col_off), B,
+                                              S, H, C.c_float(eps), _stream()), "qkv_norm_rope_bwd")
+    _count()
+    return dx
+
+
 def rope_table(cos, sin, F, H, W, D, sf, sh, sw):
     check(_l.load().b2d_rope_table(_ptr(cos), _ptr(sin), F, H, W, D, C.c_float(sf), C.c_float(sh), C.c_float(sw),
                                    _stream()), "rope_table")

@@ -118,6 +118,17 @@ int b2d_qknorm_rope_fwd(const void* src, int64_t ld, int64_t col_off, const void
 int b2d_qknorm_rope_bwd(const void* dsrc_heads, const void* x, int64_t ld, int64_t col_off, const void* weight,
                         const void* cos, const void* sin, void* dx, int64_t ld_dx, int64_t dx_col_off, int32_t B,
                         int32_t S, int32_t H, int32_t norm, float eps, void* stream);
+/* Same, for nseg (1..3) consecutive D-wide column segments of one packed row in ONE launch (q|k|v of the fused QKV
+ * projection; k|v of cross attention): segment i lives at col_off + i*D, is RMS-normed iff w_i != NULL, rotated iff bit i of
+ * rope_mask is set, and is written head-split to dst_i.  The (cos, sin) row is read once for all segments.  The backward
+ * reads the head-split upstream gradients dy_i and writes dx[row, dx_col_off + i*D + c]. */
+int b2d_qkv_norm_rope_fwd(const void* src, int64_t ld, int64_t col_off, int32_t nseg, const void* w0, const void* w1,
+                          const void* w2, int32_t rope_mask, const void* cos, const void* sin, void* dst0, void* dst1,
+                          void* dst2, int32_t B, int32_t S, int32_t H, float eps, void* stream);
+int b2d_qkv_norm_rope_bwd(const void* dy0, const void* dy1, const void* dy2, const void* x, int64_t ld, int64_t col_off,
+                          int32_t nseg, const void* w0, const void* w1, const void* w2, int32_t rope_mask, const void* cos,
+                          const void* sin, void* dx, int64_t ld_dx, int64_t dx_col_off, int32_t B, int32_t S, int32_t H,
+                          float eps, void* stream);
 
 /* RoPE table (diffusers LTXVideoRotaryPosEmbed.forward, called at patch.py:52): fp32 cos,sin [F*H*W, D/2]
  * (the reference's repeat_interleave(2) duplicates are not stored). */

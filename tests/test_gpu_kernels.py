@@ -179,6 +179,36 @@ def test_qknorm_rope_fwd_bwd(ops, which, norm, rope):
     assert rel_err(dx[:, which * D:(which + 1) * D], xf.grad.reshape(Bq * S, D)) < 1e-2
 
 
+@pytest.mark.parametrize("H,nseg", [(32, 3), (4, 3), (32, 2), (96, 3)])
+def test_qkv_norm_rope_fused_segments(ops, H, nseg):
+    """One launch for q|k|v (or k|v): segment i normed iff it has a weight, rotated iff its rope bit is set."""
+    torch.manual_seed(3)
+    Bq, S = 2, 120
+    D = H * 64
+    ang = torch.randn(S, D // 2, device="cuda")
+    cos, sin = ang.cos().repeat_interleave(2, -1).contiguous(), ang.sin().repeat_interleave(2, -1).contiguous()
+    cos_p, sin_p = ang.cos().contiguous(), ang.sin().contiguous()
+    src = rnd(Bq * S, nseg * D + 64)          # packed row with a column offset
+    ws = [(1 + 0.1 * torch.randn(D, device="cuda")).bfloat16() if i < nseg - 1 else None for i in range(nseg)]
+    mask = 0b011 if nseg == 3 else 0b01
+    dsts = [torch.empty(Bq, H, S, 64, device="cuda", dtype=torch.bfloat16) for _ in range(nseg)]
+    ops.qkv_norm_rope_fwd(src, nseg * D + 64, 64, ws, mask, cos_p, sin_p, dsts, Bq, S, H, 1e-5)
+    dys = [rnd(Bq, H, S, 64) for _ in range(nseg)]
+    dx = torch.zeros(Bq * S, nseg * D + 64, device="cuda", dtype=torch.bfloat16)
+    ops.qkv_norm_rope_bwd(dys, src, nseg * D + 64, 64, ws, mask, cos_p, sin_p, dx, nseg * D + 64, 64, Bq, S, H, 1e-5)
+    for i in range(nseg):
+        xf = src[:, 64 + i * D:64 + (i + 1) * D].float().reshape(Bq, S, D).requires_grad_(True)
+        n = F.rms_norm(xf, (D,), weight=ws[i].float(), eps=1e-5) if ws[i] is not None else xf
+        if (mask >> i) & 1:
+            xr, xi = n.unflatten(2, (-1, 2)).unbind(-1)
+            n = n * cos[None] + torch.stack([-xi, xr], dim=-1).flatten(2) * sin[None]
+        ref = n.unflatten(2, (H, 64)).transpose(1, 2)
+        assert rel_err(dsts[i], ref) < 1e-2, f"fwd seg {i}"
+        ref.backward(dys[i].float())
+        assert rel_err(dx[:, 64 + i * D:64 + (i + 1) * D], xf.grad.reshape(Bq * S, D)) < 1e-2, f"bwd seg {i}"
+    assert dx[:, :64].abs().max() == 0
+
+
 def test_golden_reference_vectors_on_gpu(ops, golden):
     """The CUDA prologue / RoPE / RMSNorm kernels against outputs of the REAL reference functions."""
     g = golden

@@ -230,6 +230,36 @@ def check_elem():
                             which * D, Bq, S, H, norm, 1e-5)
         report(f"qknorm_rope_bwd which={which}", dx[:, which * D:(which + 1) * D], xf.grad.reshape(Bq * S, D), 1e-2)
 
+    # fused 3-segment launch (q: norm+rope, k: norm+rope, v: copy) against the same references
+    wq = (1 + 0.1 * torch.randn(D, device=dev)).bfloat16(); wk = (1 + 0.1 * torch.randn(D, device=dev)).bfloat16()
+    dsts = [torch.empty(Bq, H, S, 64, device=dev, dtype=torch.bfloat16) for _ in range(3)]
+    ops.qkv_norm_rope_fwd(qkv, 3 * D, 0, (wq, wk, None), 0b011, cos_p, sin_p, dsts, Bq, S, H, 1e-5)
+    dys = [rnd(Bq, H, S, 64) for _ in range(3)]
+    dx = torch.zeros(Bq * S, 3 * D, device=dev, dtype=torch.bfloat16)
+    ops.qkv_norm_rope_bwd(dys, qkv, 3 * D, 0, (wq, wk, None), 0b011, cos_p, sin_p, dx, 3 * D, 0, Bq, S, H, 1e-5)
+    for which, wt in ((0, wq), (1, wk), (2, None)):
+        xf = qkv[:, which * D:(which + 1) * D].float().reshape(Bq, S, D).requires_grad_(True)
+        n = F.rms_norm(xf, (D,), weight=wt.float(), eps=1e-5) if wt is not None else xf
+        if which < 2:
+            xr, xi = n.unflatten(2, (-1, 2)).unbind(-1)
+            rot = torch.stack([-xi, xr], dim=-1).flatten(2)
+            n = n * cos[None] + rot * sin[None]
+        ref = n.unflatten(2, (H, 64)).transpose(1, 2)
+        report(f"qkv_norm_rope_fwd seg={which}", dsts[which], ref, 1e-2)
+        ref.backward(dys[which].float())
+        report(f"qkv_norm_rope_bwd seg={which}", dx[:, which * D:(which + 1) * D], xf.grad.reshape(Bq * S, D), 1e-2)
+    for fn, name in ((lambda: ops.qkv_norm_rope_fwd(qkv, 3 * D, 0, (wq, wk, None), 0b011, cos_p, sin_p, dsts, Bq, S, H, 1e-5), "qkv_norm_rope_fwd"),
+                     (lambda: ops.qkv_norm_rope_bwd(dys, qkv, 3 * D, 0, (wq, wk, None), 0b011, cos_p, sin_p, dx, 3 * D, 0, Bq, S, H, 1e-5), "qkv_norm_rope_bwd"),
+                     (lambda: ops.norm_modulate_fwd(x, y, tab[0], temb[:, 0:], tab[1], temb[:, D:], 6 * D, R, D, S // 2 * 2 // 2 if False else 1344, 1e-6), "norm_modulate_fwd")):
+        for _ in range(3):
+            fn()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(20):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        print(f"[time] {name} rows={Bq * S}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us (eager, may be host-bound)", flush=True)
+
     # prep + loss
     Bp, Cc = 2, 128
     lat = rnd(Bp, Cc, Fr, Hh, Ww); noise = rnd(Bp, Cc, Fr, Hh, Ww)
