@@ -58,6 +58,7 @@ constexpr int FWD_KV_STAGES = 2;
 constexpr int FWD_SMEM = TILE_BYTES /*Q*/ + FWD_KV_STAGES * 2 * TILE_BYTES /*K,V*/ + 2 * TILE_BYTES /*P*/ + 256;
 
 __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
+    griddep_launch_dependents();
     extern __shared__ uint8_t smem_fwd[];  // no static smem in this kernel: the dynamic window starts 1024-aligned
     uint8_t* smem = smem_fwd;
     if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzled tiles need a 1024-byte aligned base
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_wait();  // everything above is on-chip setup and overlaps the previous kernel's tail
     const uint32_t tmem = *tmem_slot;
     const uint32_t tS = tmem;        // 128 cols
     const uint32_t tO = tmem + 128;  // 64 cols
@@ -360,6 +362,7 @@ constexpr int FDB_P_BYTES = TILE * FDB_KV * 2;              // 16 KB (one swizzl
 constexpr int FDB_SMEM = TILE_BYTES /*Q*/ + FDB_STAGES * 2 * FDB_KV_BYTES + 2 * FDB_P_BYTES + 256;  // 112.25 KB
 
 __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __grid_constant__ AttnFwdParams p) {
+    griddep_launch_dependents();
     extern __shared__ uint8_t smem_fdb[];  // no static smem: the dynamic window starts 1024-aligned
     uint8_t* smem = smem_fdb;
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -404,6 +407,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_wait();  // everything above is on-chip setup and overlaps the previous kernel's tail
     const uint32_t tmem = *tmem_slot;  // S[b] at 64*b, O at 128
     const uint32_t tO = tmem + 128;
 
@@ -615,6 +619,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                                   const float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ nlse2,
                                   int B, int H, int Sq) {
+    griddep_launch_dependents();
+    griddep_wait();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * Sq * H * 8;
     const bool ok = t < total;
@@ -667,6 +673,7 @@ struct BwdCfg {
 
 template <bool DKV, int TY>
 __global__ void __launch_bounds__(ATT_THREADS, (TY == 64 ? 2 : 1)) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+    griddep_launch_dependents();
     using Cfg = BwdCfg<TY>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -719,6 +726,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (TY == 64 ? 2 : 1)) attn_bwd_kern
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_wait();  // everything above is on-chip setup and overlaps the previous kernel's tail
     const uint32_t tmem = *tmem_slot;
     const uint32_t tS = tmem, tDP = tmem + TY, tO1 = tmem + 2 * TY, tO2 = tmem + 2 * TY + 64;
 
@@ -947,6 +955,7 @@ constexpr int PP_SMEM = 2 * TILE_BYTES + PP_STAGES * 2 * PP_Y_BYTES + 2 * PP_NBU
 
 template <bool DKV>
 __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid_constant__ AttnBwdParams p) {
+    griddep_launch_dependents();
     constexpr int TY = PP_TY;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1003,6 +1012,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_wait();  // everything above is on-chip setup and overlaps the previous kernel's tail
     const uint32_t tmem = *tmem_slot;
     // S[k] at 128*k, dP[k] at 128*k + 64 (k = 0..2), out1 at 384, out2 at 448
     const uint32_t tO1 = tmem + 384, tO2 = tmem + 448;
@@ -1263,6 +1273,7 @@ __device__ __forceinline__ void x_load_bias(float* sBias, const float* key_bias,
 }
 
 __global__ void __launch_bounds__(X_THREADS, 1) attn_xfwd_kernel(const __grid_constant__ AttnXParams p) {
+    griddep_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;
@@ -1310,6 +1321,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xfwd_kernel(const __grid_co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_wait();  // everything above is on-chip setup and overlaps the previous kernel's tail
     const uint32_t tmem = *tmem_slot;  // S[g] at 128*g, O[g] at 256 + 64*g
 
     if (warp == 0) {
@@ -1443,6 +1455,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xfwd_kernel(const __grid_co
 }
 
 __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_constant__ AttnXParams p) {
+    griddep_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;
@@ -1495,6 +1508,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_wait();  // everything above is on-chip setup and overlaps the previous kernel's tail
     const uint32_t tmem = *tmem_slot;
     // S at 0 (128 key columns), dP at 128, dV at 256, dK at 320, dQ[j] at 384 + 64*j
     const uint32_t tDV = tmem + 256, tDK = tmem + 320;
@@ -1765,6 +1779,8 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_co
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+    griddep_launch_dependents();
+    griddep_wait();
     long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         float4 v = *reinterpret_cast<const float4*>(src + i);
@@ -1838,8 +1854,8 @@ extern "C" int b2d_attn_fwd(const void* q, const void* k, const void* v, const f
         const int ranges = min(n_qt, max(1, device_sm_count() / (B * H)));
         x.tiles_per_cta = (n_qt + ranges - 1) / ranges;
         if ((rc = set_smem((const void*)attn_xfwd_kernel, XF_SMEM, "attn_xfwd"))) return rc;
-        attn_xfwd_kernel<<<dim3((n_qt + x.tiles_per_cta - 1) / x.tiles_per_cta, B * H), X_THREADS, XF_SMEM,
-                           reinterpret_cast<cudaStream_t>(stream)>>>(x);
+        launch_k(attn_xfwd_kernel, dim3((n_qt + x.tiles_per_cta - 1) / x.tiles_per_cta, B * H), dim3(X_THREADS), XF_SMEM,
+                 reinterpret_cast<cudaStream_t>(stream), x);
         B2D_CHECK_LAUNCH("attn_xfwd");
         return 0;
     }
@@ -1847,9 +1863,9 @@ extern "C" int b2d_attn_fwd(const void* q, const void* k, const void* v, const f
     if ((rc = set_smem((const void*)attn_fwd_db_kernel, FDB_SMEM, "attn_fwd_db"))) return rc;
     dim3 grid((Sq + TILE - 1) / TILE, B * H);
     if (!force_classic && Sk > TILE)
-        attn_fwd_db_kernel<<<grid, ATT_THREADS, FDB_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+        launch_k(attn_fwd_db_kernel, grid, dim3(ATT_THREADS), FDB_SMEM, reinterpret_cast<cudaStream_t>(stream), p);
     else
-        attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+        launch_k(attn_fwd_kernel, grid, dim3(ATT_THREADS), FWD_SMEM, reinterpret_cast<cudaStream_t>(stream), p);
     B2D_CHECK_LAUNCH("attn_fwd");
     return 0;
 }
@@ -1864,8 +1880,8 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
     const bool cross = Sk <= TILE && !cross_general;
     if (!cross) {
         long long total = (long long)B * Sq * H * 8;
-        attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-            (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, lse, delta_ws, delta_ws + (long long)B * H * Sq, B, H, Sq);
+        launch_k(attn_delta_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const __nv_bfloat16*)out,
+                 (const __nv_bfloat16*)dout, lse, delta_ws, delta_ws + (long long)B * H * Sq, B, H, Sq);
         B2D_CHECK_LAUNCH("attn_delta");
     }
     constexpr int TY = 64;
@@ -1900,7 +1916,7 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
             if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "attn_bwd memset: %s", cudaGetErrorString(e));
         }
         if ((rc = set_smem((const void*)attn_xbwd_kernel, XB_SMEM, "attn_xbwd"))) return rc;
-        attn_xbwd_kernel<<<dim3(gx, B * H), X_THREADS, XB_SMEM, st>>>(x);
+        launch_k(attn_xbwd_kernel, dim3(gx, B * H), dim3(X_THREADS), XB_SMEM, st, x);
         B2D_CHECK_LAUNCH("attn_xbwd");
         return 0;
     }
@@ -1929,18 +1945,18 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
         cudaError_t e = cudaMemsetAsync(p.acc1, 0, 2 * n_kv * sizeof(float), st);
         if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "attn_bwd memset: %s", cudaGetErrorString(e));
         if (use_pp)
-            attn_bwd_pp_kernel<true><<<dim3((Sk + TILE - 1) / TILE, B * H, splits), PP_THREADS, PP_SMEM, st>>>(p);
+            launch_k(attn_bwd_pp_kernel<true>, dim3((Sk + TILE - 1) / TILE, B * H, splits), dim3(PP_THREADS), PP_SMEM, st, p);
         else
-            attn_bwd_kernel<true, TY><<<dim3((Sk + TILE - 1) / TILE, B * H, splits), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
+            launch_k(attn_bwd_kernel<true, TY>, dim3((Sk + TILE - 1) / TILE, B * H, splits), dim3(ATT_THREADS), BwdCfg<TY>::SMEM, st, p);
         B2D_CHECK_LAUNCH("attn_bwd_dkv(split)");
-        f32_to_bf16_kernel<<<(unsigned)((n_kv / 4 + 255) / 256), 256, 0, st>>>(p.acc1, (__nv_bfloat16*)dv, n_kv);
-        f32_to_bf16_kernel<<<(unsigned)((n_kv / 4 + 255) / 256), 256, 0, st>>>(p.acc2, (__nv_bfloat16*)dk, n_kv);
+        launch_k(f32_to_bf16_kernel, dim3((unsigned)((n_kv / 4 + 255) / 256)), dim3(256), 0, st, p.acc1, (__nv_bfloat16*)dv, n_kv);
+        launch_k(f32_to_bf16_kernel, dim3((unsigned)((n_kv / 4 + 255) / 256)), dim3(256), 0, st, p.acc2, (__nv_bfloat16*)dk, n_kv);
         B2D_CHECK_LAUNCH("attn_bwd_dkv(convert)");
     } else {
         if (use_pp)
-            attn_bwd_pp_kernel<true><<<dim3((Sk + TILE - 1) / TILE, B * H), PP_THREADS, PP_SMEM, st>>>(p);
+            launch_k(attn_bwd_pp_kernel<true>, dim3((Sk + TILE - 1) / TILE, B * H), dim3(PP_THREADS), PP_SMEM, st, p);
         else
-            attn_bwd_kernel<true, TY><<<dim3((Sk + TILE - 1) / TILE, B * H), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
+            launch_k(attn_bwd_kernel<true, TY>, dim3((Sk + TILE - 1) / TILE, B * H), dim3(ATT_THREADS), BwdCfg<TY>::SMEM, st, p);
         B2D_CHECK_LAUNCH("attn_bwd_dkv");
     }
     p.acc1 = p.acc2 = nullptr;
@@ -1950,9 +1966,9 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
     p.y_per_split = (Sk + TY - 1) / TY;
     if ((rc = set_smem((const void*)attn_bwd_kernel<false, TY>, BwdCfg<TY>::SMEM, "attn_bwd_dq"))) return rc;
     if (use_pp)
-        attn_bwd_pp_kernel<false><<<dim3((Sq + TILE - 1) / TILE, B * H), PP_THREADS, PP_SMEM, st>>>(p);
+        launch_k(attn_bwd_pp_kernel<false>, dim3((Sq + TILE - 1) / TILE, B * H), dim3(PP_THREADS), PP_SMEM, st, p);
     else
-        attn_bwd_kernel<false, TY><<<dim3((Sq + TILE - 1) / TILE, B * H), ATT_THREADS, BwdCfg<TY>::SMEM, st>>>(p);
+        launch_k(attn_bwd_kernel<false, TY>, dim3((Sq + TILE - 1) / TILE, B * H), dim3(ATT_THREADS), BwdCfg<TY>::SMEM, st, p);
     B2D_CHECK_LAUNCH("attn_bwd_dq");
     return 0;
 }

@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_fwd_kernel(
     const __nv_bfloat16* __restrict__ shift_emb, const __nv_bfloat16* __restrict__ scale_tab,
     const __nv_bfloat16* __restrict__ scale_emb, long long emb_stride, int D, int rows_per_sample, float eps,
     int layer_norm) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int row = blockIdx.x;
     const int b = row / rows_per_sample;
     const __nv_bfloat16* xr = x + (long long)row * D;
@@ -125,6 +127,8 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
     const __nv_bfloat16* __restrict__ scale_emb, const __nv_bfloat16* __restrict__ gate2_tab,
     const __nv_bfloat16* __restrict__ gate2_emb, __nv_bfloat16* __restrict__ out2, long long emb_stride, int D,
     int rows_per_sample, float eps, int layer_norm) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int row = blockIdx.x;
     const int b = row / rows_per_sample;
     const long long ro = (long long)row * D;
@@ -220,6 +224,8 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
 __global__ void colscale_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                 const __nv_bfloat16* __restrict__ tab, const __nv_bfloat16* __restrict__ emb,
                                 long long emb_stride, long long total8, int D, int rows_per_sample) {
+    griddep_launch_dependents();
+    griddep_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total8) return;
     long long e0 = i * 8;
@@ -252,6 +258,8 @@ template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS) qkv_norm_rope_fwd_kernel(
     const __nv_bfloat16* __restrict__ src, long long ld, long long col_off, const QkvSegArgs a,
     const float* __restrict__ cosT, const float* __restrict__ sinT, int S, int H, float eps) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int D = H * 64;
     const int row = blockIdx.x;
     const int b = row / S, s = row % S;
@@ -342,6 +350,8 @@ __global__ void __launch_bounds__(ROW_THREADS) qkv_norm_rope_bwd_kernel(
     const __nv_bfloat16* __restrict__ x, long long ld, long long col_off, const QkvSegArgs a,
     const float* __restrict__ cosT, const float* __restrict__ sinT, __nv_bfloat16* __restrict__ dx, long long ld_dx,
     long long dx_col_off, int S, int H, float eps) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int D = H * 64;
     const int row = blockIdx.x;
     const int b = row / S, s = row % S;
@@ -632,9 +642,9 @@ using namespace b2d;
 #define ROW_DISPATCH(D_, KERNEL, GRID, ...)                                             \
     do {                                                                                \
         const int nch__ = ((D_) + 8 * ROW_THREADS - 1) / (8 * ROW_THREADS);             \
-        if (nch__ <= 1) KERNEL<1><<<GRID, ROW_THREADS, 0, STREAM>>>(__VA_ARGS__);       \
-        else if (nch__ == 2) KERNEL<2><<<GRID, ROW_THREADS, 0, STREAM>>>(__VA_ARGS__);  \
-        else KERNEL<4><<<GRID, ROW_THREADS, 0, STREAM>>>(__VA_ARGS__);                  \
+        if (nch__ <= 1) launch_k(KERNEL<1>, dim3(GRID), dim3(ROW_THREADS), 0, STREAM, __VA_ARGS__);       \
+        else if (nch__ == 2) launch_k(KERNEL<2>, dim3(GRID), dim3(ROW_THREADS), 0, STREAM, __VA_ARGS__);  \
+        else launch_k(KERNEL<4>, dim3(GRID), dim3(ROW_THREADS), 0, STREAM, __VA_ARGS__);                  \
     } while (0)
 
 static int check_rowop(int rows, int D, int rps) {
@@ -674,10 +684,9 @@ extern "C" int b2d_colscale(const void* x, void* out, const void* tab, const voi
     B2D_BIND(x);
     if (D % 8) return set_error(B2D_ERR_SHAPE, "colscale: D %% 8");
     long long total8 = (long long)rows * D / 8;
-    colscale_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, STREAM>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out,
-                                                                          (const __nv_bfloat16*)tab,
-                                                                          (const __nv_bfloat16*)emb, emb_stride, total8,
-                                                                          D, rows_per_sample);
+    launch_k(colscale_kernel, dim3((unsigned)((total8 + 255) / 256)), dim3(256), 0, STREAM, (const __nv_bfloat16*)x,
+             (__nv_bfloat16*)out, (const __nv_bfloat16*)tab, (const __nv_bfloat16*)emb, emb_stride, total8, D,
+             rows_per_sample);
     B2D_CHECK_LAUNCH("colscale");
     return 0;
 }

@@ -68,6 +68,7 @@ __device__ __forceinline__ uint4 ld_global_16B(const void* p) {
 
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmKParams p) {
+    griddep_launch_dependents();
     using Cfg = GemmCfg<BN, B_MN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_wait();  // everything above is on-chip setup and overlaps the previous kernel's tail
     const uint32_t tmem_base = *tmem_slot;
 
     const int kb_total = p.kb_main + p.kb_ext;  // per work item when splits == 1
@@ -431,7 +433,7 @@ static int launch_gemm(const GemmKParams& kp, int grid, cudaStream_t stream) {
         if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
         attr_set[dev] = true;
     }
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(kp);
+    launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, kp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
     return B2D_OK;

@@ -31,6 +31,28 @@ int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long c
 int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                  const uint32_t* box, int elem_bytes, int swizzle128);
 
+// Programmatic dependent launch: kernels started through launch_k carry cudaLaunchAttributeProgrammaticStreamSerialization,
+// so the grid is pre-launched while its stream predecessor drains (its on-chip prologue - barrier init, TMEM allocation,
+// tensor-map prefetch - overlaps the predecessor's tail) and blocks in griddepcontrol.wait until the predecessor has
+// completed and flushed.  ONLY kernels that execute griddep_wait() before their first global access may be launched
+// this way.  Off by default (B2D_PDL=1 turns it on): see pdl_enabled() for the measurement.  Works under stream capture.
+bool pdl_enabled();
+
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+
 #define B2D_CHECK_LAUNCH(name)                                                                     \
     do {                                                                                           \
         cudaError_t e__ = cudaGetLastError();                                                      \
