@@ -252,6 +252,8 @@ struct QkvSegArgs {
     __nv_bfloat16* dst[3];       // fwd: head-split outputs;  bwd: head-split upstream gradients (read)
     int nseg;
     int rope_mask;               // bit i: segment i is rotated
+    int rows_per_w;              // > 0: rows are stacked DiT blocks, row r uses weights w[i] + (r / rows_per_w) * w_stride
+    long long w_stride;
 };
 
 template <int NCH>
@@ -264,6 +266,7 @@ __global__ void __launch_bounds__(ROW_THREADS) qkv_norm_rope_fwd_kernel(
     const int row = blockIdx.x;
     const int b = row / S, s = row % S;
     const __nv_bfloat16* xr = src + (long long)row * ld + col_off;
+    const long long woff = a.rows_per_w > 0 ? (long long)(row / a.rows_per_w) * a.w_stride : 0;
     uint4 xq[3][NCH], wq[3][NCH];
     float4 c4[NCH], s4[NCH];
 #pragma unroll
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(ROW_THREADS) qkv_norm_rope_fwd_kernel(
             for (int i = 0; i < 3; ++i) {
                 if (i < a.nseg) {
                     xq[i][c] = ldg16(xr + (long long)i * D + col);
-                    if (a.w[i] != nullptr) wq[i][c] = ldg16(a.w[i] + col);
+                    if (a.w[i] != nullptr) wq[i][c] = ldg16(a.w[i] + woff + col);
                 }
             }
             if (a.rope_mask) {
@@ -356,6 +359,7 @@ __global__ void __launch_bounds__(ROW_THREADS) qkv_norm_rope_bwd_kernel(
     const int row = blockIdx.x;
     const int b = row / S, s = row % S;
     const __nv_bfloat16* xr = x + (long long)row * ld + col_off;
+    const long long woff = a.rows_per_w > 0 ? (long long)(row / a.rows_per_w) * a.w_stride : 0;
     uint4 xq[3][NCH], wq[3][NCH], dq[3][NCH];
     float4 c4[NCH], s4[NCH];
 #pragma unroll
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(ROW_THREADS) qkv_norm_rope_bwd_kernel(
                     dq[i][c] = ldg16(a.dst[i] + (((long long)b * H + h) * S + s) * 64 + d);
                     if (a.w[i] != nullptr) {
                         xq[i][c] = ldg16(xr + (long long)i * D + col);
-                        wq[i][c] = ldg16(a.w[i] + col);
+                        wq[i][c] = ldg16(a.w[i] + woff + col);
                     }
                 }
             }
@@ -747,20 +751,23 @@ extern "C" int b2d_qknorm_rope_bwd(const void* dsrc_heads, const void* x, int64_
 extern "C" int b2d_qkv_norm_rope_fwd(const void* src, int64_t ld, int64_t col_off, int32_t nseg, const void* w0,
                                      const void* w1, const void* w2, int32_t rope_mask, const void* cos, const void* sin,
                                      void* dst0, void* dst1, void* dst2, int32_t B, int32_t S, int32_t H, float eps,
-                                     void* stream) {
+                                     int32_t rows_per_w, int64_t w_stride, void* stream) {
     B2D_BIND(src);
     QkvSegArgs a = {};
     a.nseg = nseg;
     a.w[0] = (const __nv_bfloat16*)w0; a.w[1] = (const __nv_bfloat16*)w1; a.w[2] = (const __nv_bfloat16*)w2;
     a.dst[0] = (__nv_bfloat16*)dst0; a.dst[1] = (__nv_bfloat16*)dst1; a.dst[2] = (__nv_bfloat16*)dst2;
     a.rope_mask = rope_mask;
+    a.rows_per_w = rows_per_w; a.w_stride = w_stride;
+    if (rows_per_w < 0 || (w_stride % 8) != 0) return set_error(B2D_ERR_ARG, "qkv_norm_rope: bad weight stacking");
     return launch_qkv_fwd(src, ld, col_off, a, cos, sin, B, S, H, eps, stream);
 }
 
 extern "C" int b2d_qkv_norm_rope_bwd(const void* dy0, const void* dy1, const void* dy2, const void* x, int64_t ld,
                                      int64_t col_off, int32_t nseg, const void* w0, const void* w1, const void* w2,
                                      int32_t rope_mask, const void* cos, const void* sin, void* dx, int64_t ld_dx,
-                                     int64_t dx_col_off, int32_t B, int32_t S, int32_t H, float eps, void* stream) {
+                                     int64_t dx_col_off, int32_t B, int32_t S, int32_t H, float eps, int32_t rows_per_w,
+                                     int64_t w_stride, void* stream) {
     B2D_BIND(dy0);
     QkvSegArgs a = {};
     a.nseg = nseg;
@@ -769,6 +776,8 @@ extern "C" int b2d_qkv_norm_rope_bwd(const void* dy0, const void* dy1, const voi
     a.dst[1] = (__nv_bfloat16*)const_cast<void*>(dy1);
     a.dst[2] = (__nv_bfloat16*)const_cast<void*>(dy2);
     a.rope_mask = rope_mask;
+    a.rows_per_w = rows_per_w; a.w_stride = w_stride;
+    if (rows_per_w < 0 || (w_stride % 8) != 0) return set_error(B2D_ERR_ARG, "qkv_norm_rope_bwd: bad weight stacking");
     return launch_qkv_bwd(x, ld, col_off, a, cos, sin, dx, ld_dx, dx_col_off, B, S, H, eps, stream);
 }
 

@@ -25,7 +25,8 @@ struct GemmKParams {
     int a2_group_n;
     int splits, batch;
     int a_brow, a_bcol, b_brow, b_bcol;
-    long long c_boff;
+    int a2_brow, b2_brow;
+    long long c_boff, bias_boff;
     int epi;
     float alpha;
     void* out;
@@ -156,13 +157,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                         const int k2 = (i - (kb_end - kb_begin)) * BLOCK_K;
                         const int a2off = p.a2_group_n > 0 ? (n0 / p.a2_group_n) * p.K2 : 0;
                         // A2 is always K-major [M, *]; B2 follows B's majorness
-                        tma_load_2d(sA, &p.tmA2, &full_bar[stage], k2 + a2off, m0);
+                        tma_load_2d(sA, &p.tmA2, &full_bar[stage], k2 + a2off, m0 + z * p.a2_brow);
                         if (B_MN == 0) {
-                            tma_load_2d(sB, &p.tmB2, &full_bar[stage], k2, n0);
+                            tma_load_2d(sB, &p.tmB2, &full_bar[stage], k2, n0 + z * p.b2_brow);
                         } else {
 #pragma unroll
                             for (int j = 0; j < (BN + 63) / 64; ++j)
-                                tma_load_2d(sB + j * 8192, &p.tmB2, &full_bar[stage], n0 + 64 * j, k2);
+                                tma_load_2d(sB + j * 8192, &p.tmB2, &full_bar[stage], n0 + 64 * j, k2 + z * p.b2_brow);
                         }
                     }
                     if (++stage == Cfg::STAGES) {
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 #pragma unroll
                             for (int j8 = 0; j8 < 4; ++j8) {
                                 if (col0 + j8 * 8 < p.N) {
-                                    uint4 bb = ld_global_16B(p.bias + col0 + j8 * 8);
+                                    uint4 bb = ld_global_16B(p.bias + (long long)z * p.bias_boff + col0 + j8 * 8);
                                     const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) {
@@ -530,12 +531,13 @@ extern "C" int b2d_gemm(const b2d_gemm_desc* d, void* stream_v) {
         if (d->K2 > 0) {
             if (d->A2 == nullptr || d->B2 == nullptr) return set_error(B2D_ERR_ARG, "gemm: K2>0 needs A2,B2");
             int groups = d->a2_group_n > 0 ? (d->N + d->a2_group_n - 1) / d->a2_group_n : 1;
-            rc = make_tmap_2d(&kp.tmA2, d->A2, d->M, (long long)d->K2 * groups, d->lda2, BLOCK_M, 64);
+            rc = make_tmap_2d(&kp.tmA2, d->A2, (long long)d->M + (batch - 1) * d->a2_boff_row, (long long)d->K2 * groups,
+                              d->lda2, BLOCK_M, 64);
             if (rc) return rc;
             if (d->b_mn_major)
-                rc = make_tmap_2d(&kp.tmB2, d->B2, d->K2, d->N, d->ldb2, 64, 64);
+                rc = make_tmap_2d(&kp.tmB2, d->B2, (long long)d->K2 + (batch - 1) * d->b2_boff_row, d->N, d->ldb2, 64, 64);
             else
-                rc = make_tmap_2d(&kp.tmB2, d->B2, d->N, d->K2, d->ldb2, bn, 64);
+                rc = make_tmap_2d(&kp.tmB2, d->B2, (long long)d->N + (batch - 1) * d->b2_boff_row, d->K2, d->ldb2, bn, 64);
             if (rc) return rc;
         }
     }
@@ -545,6 +547,10 @@ extern "C" int b2d_gemm(const b2d_gemm_desc* d, void* stream_v) {
     kp.a_brow = (int)d->a_boff_row; kp.a_bcol = (int)d->a_boff_col;
     kp.b_brow = (int)d->b_boff_row; kp.b_bcol = (int)d->b_boff_col;
     kp.c_boff = d->c_boff;
+    kp.a2_brow = (int)d->a2_boff_row; kp.b2_brow = (int)d->b2_boff_row;
+    kp.bias_boff = d->bias_boff;
+    if (d->a2_boff_row < 0 || d->b2_boff_row < 0 || d->bias_boff < 0 || (d->bias_boff % 8) != 0)
+        return set_error(B2D_ERR_ARG, "gemm: extension/bias batch offsets must be >= 0 (bias_boff a multiple of 8)");
     kp.epi = d->epi;
     kp.alpha = d->alpha == 0.f ? 1.f : d->alpha;
     kp.out = d->out; kp.ldc = d->ldc;

@@ -44,6 +44,7 @@ class GemmDesc(C.Structure):
         ("rows_per_sample", C.c_int32),
         ("block_n", C.c_int32),
         ("max_ctas", C.c_int32),
+        ("a2_boff_row", C.c_int64), ("b2_boff_row", C.c_int64), ("bias_boff", C.c_int64),
     ]
 
 

@@ -264,13 +264,23 @@ class B200LTXTransformer(nn.Module):
             self.lora_flat = torch.zeros(nl * per_blk, dtype=torch.float32, device=dev)
             self.lora_grad_flat = torch.zeros_like(self.lora_flat)
             self.lora_bf16 = torch.zeros(nl * per_blk, dtype=torch.bfloat16, device=dev)
+        # the text-side K/V projection of cross attention reads only the caption embedding, so all blocks' [Wk2;Wv2], biases
+        # and norm_k weights are stacked: one batched launch per step instead of one per block
+        wdt = self.proj_in.weight.dtype
+        self._Wkv2_all = torch.empty(nl, 2 * d, d, dtype=wdt, device=dev)
+        self._bkv2_all = torch.empty(nl, 2 * d, dtype=wdt, device=dev)
+        self._nk2_all = torch.empty(nl, d, dtype=wdt, device=dev)
         for li, blk in enumerate(self.transformer_blocks):
             a1, a2 = blk.attn1, blk.attn2
             e = {}
             # fused base weights; the module parameters become views of the packed storage
-            def pack(mods):
-                w = torch.cat([_base(m).weight.data for m in mods], 0).contiguous()
-                bvec = torch.cat([_base(m).bias.data for m in mods], 0).contiguous()
+            def pack(mods, w=None, bvec=None):
+                if w is None:
+                    w = torch.cat([_base(m).weight.data for m in mods], 0).contiguous()
+                    bvec = torch.cat([_base(m).bias.data for m in mods], 0).contiguous()
+                else:
+                    w.copy_(torch.cat([_base(m).weight.data for m in mods], 0))
+                    bvec.copy_(torch.cat([_base(m).bias.data for m in mods], 0))
                 o = 0
                 for m in mods:
                     n = _base(m).out_features
@@ -281,7 +291,9 @@ class B200LTXTransformer(nn.Module):
             e["Wqkv"], e["bqkv"] = pack([a1.to_q, a1.to_k, a1.to_v])
             e["Wo"], e["bo"] = _base(a1.to_out[0]).weight.data, _base(a1.to_out[0]).bias.data
             e["Wq2"], e["bq2"] = _base(a2.to_q).weight.data, _base(a2.to_q).bias.data
-            e["Wkv2"], e["bkv2"] = pack([a2.to_k, a2.to_v])
+            e["Wkv2"], e["bkv2"] = pack([a2.to_k, a2.to_v], self._Wkv2_all[li], self._bkv2_all[li])
+            self._nk2_all[li].copy_(a2.norm_k.weight.data)
+            a2.norm_k.weight.data = self._nk2_all[li]
             e["Wo2"], e["bo2"] = _base(a2.to_out[0]).weight.data, _base(a2.to_out[0]).bias.data
             e["W1"], e["b1"] = blk.ff.net[0].proj.weight.data, blk.ff.net[0].proj.bias.data
             e["W2"], e["b2"] = blk.ff.net[2].weight.data, blk.ff.net[2].bias.data
@@ -380,7 +392,7 @@ class B200LTXTransformer(nn.Module):
         z("n2", R, d); z("f", R, cfg.ffn_mult * d); z("y", R, d); z("pred", R, cfg.out_channels)
         z("dh", R, d); z("g", R, d); z("dwide", R, cfg.ffn_mult * d); z("dn", R, d); z("da", R, d)
         z("dqh", B, H, S, 64); z("dkh", B, H, S, 64); z("dvh", B, H, S, 64)
-        z("dk2h", B, H, L, 64); z("dv2h", B, H, L, 64)
+        z("dk2h", nl, B, H, L, 64); z("dv2h", nl, B, H, L, 64)   # kept per block: one batched norm-bwd at the end
         z("delta", max(ops.attn_bwd_ws_floats(B, H, S, S), ops.attn_bwd_ws_floats(B, H, S, L)), kw=f32)
         self._ws[key] = ws
         return ws
@@ -472,6 +484,23 @@ class B200LTXTransformer(nn.Module):
         enc = ws["enc"]
         ops.gemm(x_in, self.proj_in.weight, ws["h"][0], M=R, N=d, K=Cin, bias=self.proj_in.bias)
         scale = 1.0 / math.sqrt(cfg.attention_head_dim)
+        # ---- cross-attention K/V of ALL blocks (functions of `enc` only): LoRA-down, fused [Wk2;Wv2] projection with the
+        # LoRA-up K-extension, and k-norm + head split, each as ONE block-batched launch
+        ops.CONTEXT = "f.kv2"
+        e0, pb = self._blk[0], self._per_blk
+        kv2_all = ws["kv2"].view(nl * RL, 2 * d)
+        if rp:
+            u_all = ws["u_kv2"].view(nl * RL, 2 * rp)
+            ops.gemm(enc, e0["Ab_kv2"], u_all, M=RL, N=2 * rp, K=d, batch=nl, b_boff=(pb // d, 0), c_boff=RL * 2 * rp,
+                     alpha=self.lora_scaling, tag="lora_u")
+            ops.gemm(enc, self._Wkv2_all.view(nl * 2 * d, d), kv2_all, M=RL, N=2 * d, K=d, bias=self._bkv2_all, batch=nl,
+                     b_boff=(2 * d, 0), c_boff=RL * 2 * d, bias_boff=2 * d, A2=u_all, B2=e0["Bb_kv2"], K2=rp, a2_group_n=d,
+                     a2_boff_row=RL, b2_boff_row=pb // rp)
+        else:
+            ops.gemm(enc, self._Wkv2_all.view(nl * 2 * d, d), kv2_all, M=RL, N=2 * d, K=d, bias=self._bkv2_all, batch=nl,
+                     b_boff=(2 * d, 0), c_boff=RL * 2 * d, bias_boff=2 * d)
+        ops.qkv_norm_rope_fwd(kv2_all, 2 * d, 0, (self._nk2_all, None), 0, None, None, (ws["k2h"], ws["v2h"]), nl * B, L, H,
+                              cfg.qk_norm_eps, rows_per_w=RL, w_stride=d)
         for l in range(nl):
             e = self._blk[l]
             sst = e["sst"]
@@ -497,11 +526,7 @@ class B200LTXTransformer(nn.Module):
             h1 = ws["h1"][l]
             self._lin(h1, e["Wq2"], e["bq2"], ws["q2"][l], R, d, d,
                       lora=(e["Ab_q2"], e["Bb_q2"], ws["u_q2"][l], 1) if rp else None)
-            self._lin(enc, e["Wkv2"], e["bkv2"], ws["kv2"][l], RL, 2 * d, d,
-                      lora=(e["Ab_kv2"], e["Bb_kv2"], ws["u_kv2"][l], 2) if rp else None)
             ops.qknorm_rope_fwd(ws["q2"][l], d, 0, e["nq2"], None, None, ws["q2h"][l], B, S, H, True, cfg.qk_norm_eps)
-            ops.qkv_norm_rope_fwd(ws["kv2"][l], 2 * d, 0, (e["nk2"], None), 0, None, None, (ws["k2h"][l], ws["v2h"][l]),
-                                  B, L, H, cfg.qk_norm_eps)
             ops.attn_fwd(ws["q2h"][l], ws["k2h"][l], ws["v2h"][l], key_bias, ws["ao2"][l], ws["lse2"][l], B, H, S, L, scale)
             self._lin(ws["ao2"][l], e["Wo2"], e["bo2"], ws["h2"][l], R, d, d,
                       lora=(e["Ab_o2"], e["Bb_o2"], ws["u_o2"][l], 1) if rp else None,
@@ -613,11 +638,9 @@ class B200LTXTransformer(nn.Module):
             du = self._lora_du(dh2, ws["du_o2"][l], e, "o2", R, d, 1)
             ops.gemm(dh2, e["Wo2"], ws["da"], M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_o2"], K2=rp)
             ops.attn_bwd(ws["q2h"][l], ws["k2h"][l], ws["v2h"][l], key_bias, ws["ao2"][l], ws["da"], ws["lse2"][l],
-                         ws["delta"], ws["dqh"], ws["dk2h"], ws["dv2h"], B, H, S, L, scale)
+                         ws["delta"], ws["dqh"], ws["dk2h"][l], ws["dv2h"][l], B, H, S, L, scale)
             ops.qknorm_rope_bwd(ws["dqh"], ws["q2"][l], d, 0, e["nq2"], None, None, dq2, d, 0, B, S, H, True,
                                 cfg.qk_norm_eps)
-            ops.qkv_norm_rope_bwd((ws["dk2h"], ws["dv2h"]), ws["kv2"][l], 2 * d, 0, (e["nk2"], None), 0, None, None, dkv2,
-                                  2 * d, 0, B, L, H, cfg.qk_norm_eps)
             du = self._lora_du(dq2, ws["du_q2"][l], e, "q2", R, d, 1)
             # dh1 = dh2 + dq2 W_q2 + du A ; gated copy (gate_msa, row 2) = dy of the self-attention out-proj
             ops.gemm(dq2, e["Wq2"], dh, M=R, N=d, K=d, b_mn=True, A2=du, B2=e["Ab_q2"], K2=rp,
@@ -640,6 +663,11 @@ class B200LTXTransformer(nn.Module):
             ops.norm_modulate_bwd(ws["dn"], ws["h"][l], dh, dh, sst[1], temb[:, d:], 6 * d, R, d, S, cfg.norm_eps,
                                   gate2_tab=prev[5] if l > 0 else None, gate2_emb=temb[:, 5 * d:] if l > 0 else None,
                                   out2=g if l > 0 else None)
+        # text-side k-norm backward of all blocks in one launch (its output only feeds the adapter gradients below)
+        ops.CONTEXT = "b.kv2"
+        ops.qkv_norm_rope_bwd((ws["dk2h"], ws["dv2h"]), ws["kv2"].view(nl * RL, 2 * d), 2 * d, 0, (self._nk2_all, None), 0,
+                              None, None, ws["dy_kv2"].view(nl * RL, 2 * d), 2 * d, 0, nl * B, L, H, cfg.qk_norm_eps,
+                              rows_per_w=RL, w_stride=d)
         ops.CONTEXT = "b.wgrad"
         self._lora_wgrads_all(ws, R, RL)
         ops.CONTEXT = ""

@@ -63,7 +63,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          a_mn=False, b_mn=False, A2=None, B2=None, K2=0, lda2=None, ldb2=None, a2_group_n=0, splits=1, batch=1,
          a_boff=(0, 0), b_boff=(0, 0), c_boff=0, epi=EPI_STORE, alpha=1.0, out2=None, ldc2=None, bias=None, res=None,
          ldres=None, aux=None, ldaux=None, gate_table=None, gate_temb=None, gate2_table=None, gate2_temb=None,
-         temb_stride=0, rows_per_sample=0, block_n=0, max_ctas=0, tag="gemm"):
+         temb_stride=0, rows_per_sample=0, block_n=0, max_ctas=0, a2_boff_row=0, b2_boff_row=0, bias_boff=0,
+         tag="gemm"):
     """C = epilogue(alpha * (opA(A) opB(B)^T + A2 B2^T)).  See include/b2d.h b2d_gemm_desc."""
     d = GemmDesc()
     d.A = A.data_ptr(); d.lda = lda if lda is not None else A.stride(0)
@@ -97,6 +98,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     d.rows_per_sample = rows_per_sample
     d.block_n = block_n
     d.max_ctas = max_ctas
+    d.a2_boff_row, d.b2_boff_row, d.bias_boff = a2_boff_row, b2_boff_row, bias_boff
     with _Timed(tag):
         check(_l.load().b2d_gemm(C.byref(d), _stream()), "gemm")
     _count()
@@ -150,7 +152,7 @@ def qknorm_rope_bwd(dyh, x, ld, col_off, weight, cos, sin, dx, ld_dx, dx_col_off
     return dx
 
 
-def qkv_norm_rope_fwd(src, ld, col_off, weights, rope_mask, cos, sin, dsts, B, S, H, eps):
+def qkv_norm_rope_fwd(src, ld, col_off, weights, rope_mask, cos, sin, dsts, B, S, H, eps, rows_per_w=0, w_stride=0):
     """nseg = len(dsts) consecutive D-wide segments of src rows -> head-split dsts in ONE launch (b2d.h)."""
     n = len(dsts)
     w = list(weights) + [None] * (3 - n)
@@ -158,11 +160,13 @@ def qkv_norm_rope_fwd(src, ld, col_off, weights, rope_mask, cos, sin, dsts, B, S
     with _Timed("qknorm_rope_fwd"):
         check(_l.load().b2d_qkv_norm_rope_fwd(_ptr(src), C.c_int64(ld), C.c_int64(col_off), n, _ptr(w[0]), _ptr(w[1]),
                                               _ptr(w[2]), int(rope_mask), _ptr(cos), _ptr(sin), _ptr(d[0]), _ptr(d[1]),
-                                              _ptr(d[2]), B, S, H, C.c_float(eps), _stream()), "qkv_norm_rope_fwd")
+                                              _ptr(d[2]), B, S, H, C.c_float(eps), int(rows_per_w), C.c_int64(w_stride),
+                                              _stream()), "qkv_norm_rope_fwd")
     _count()
 
 
-def qkv_norm_rope_bwd(dys, x, ld, col_off, weights, rope_mask, cos, sin, dx, ld_dx, dx_col_off, B, S, H, eps):
+def qkv_norm_rope_bwd(dys, x, ld, col_off, weights, rope_mask, cos, sin, dx, ld_dx, dx_col_off, B, S, H, eps,
+                      rows_per_w=0, w_stride=0):
     n = len(dys)
     w = list(weights) + [None] * (3 - n)
     d = list(dys) + [None] * (3 - n)
@@ -170,7 +174,8 @@ def qkv_norm_rope_bwd(dys, x, ld, col_off, weights, rope_mask, cos, sin, dx, ld_
         check(_l.load().b2d_qkv_norm_rope_bwd(_ptr(d[0]), _ptr(d[1]), _ptr(d[2]), _ptr(x), C.c_int64(ld),
                                               C.c_int64(col_off), n, _ptr(w[0]), _ptr(w[1]), _ptr(w[2]), int(rope_mask),
                                               _ptr(cos), _ptr(sin), _ptr(dx), C.c_int64(ld_dx), C.c_int64(dx_col_off), B,
-                                              S, H, C.c_float(eps), _stream()), "qkv_norm_rope_bwd")
+                                              S, H, C.c_float(eps), int(rows_per_w), C.c_int64(w_stride), _stream()),
+              "qkv_norm_rope_bwd")
     _count()
     return dx
 

@@ -81,6 +81,9 @@ typedef struct {
   int32_t rows_per_sample;          /* b = row / rows_per_sample */
   int32_t block_n;                  /* 0 = auto; else 64/128/192/256 */
   int32_t max_ctas;                 /* 0 = #SMs */
+  /* batch offsets of the extension operands and of the bias (batch z reads A2 rows + z*a2_boff_row, B2 rows
+   * + z*b2_boff_row, bias + z*bias_boff elements): one launch covers the same projection of several DiT blocks */
+  int64_t a2_boff_row, b2_boff_row, bias_boff;
 } b2d_gemm_desc;
 
 int b2d_gemm(const b2d_gemm_desc* d, void* stream);
@@ -121,14 +124,17 @@ int b2d_qknorm_rope_bwd(const void* dsrc_heads, const void* x, int64_t ld, int64
 /* Same, for nseg (1..3) consecutive D-wide column segments of one packed row in ONE launch (q|k|v of the fused QKV
  * projection; k|v of cross attention): segment i lives at col_off + i*D, is RMS-normed iff w_i != NULL, rotated iff bit i of
  * rope_mask is set, and is written head-split to dst_i.  The (cos, sin) row is read once for all segments.  The backward
- * reads the head-split upstream gradients dy_i and writes dx[row, dx_col_off + i*D + c]. */
+ * reads the head-split upstream gradients dy_i and writes dx[row, dx_col_off + i*D + c].
+ * rows_per_w > 0: the rows are several DiT blocks stacked (B = blocks * batch); row r then uses the norm weights
+ * w_i + (r / rows_per_w) * w_stride (elements) - the text-side k|v of all blocks in one launch. */
 int b2d_qkv_norm_rope_fwd(const void* src, int64_t ld, int64_t col_off, int32_t nseg, const void* w0, const void* w1,
                           const void* w2, int32_t rope_mask, const void* cos, const void* sin, void* dst0, void* dst1,
-                          void* dst2, int32_t B, int32_t S, int32_t H, float eps, void* stream);
+                          void* dst2, int32_t B, int32_t S, int32_t H, float eps, int32_t rows_per_w, int64_t w_stride,
+                          void* stream);
 int b2d_qkv_norm_rope_bwd(const void* dy0, const void* dy1, const void* dy2, const void* x, int64_t ld, int64_t col_off,
                           int32_t nseg, const void* w0, const void* w1, const void* w2, int32_t rope_mask, const void* cos,
                           const void* sin, void* dx, int64_t ld_dx, int64_t dx_col_off, int32_t B, int32_t S, int32_t H,
-                          float eps, void* stream);
+                          float eps, int32_t rows_per_w, int64_t w_stride, void* stream);
 
 /* RoPE table (diffusers LTXVideoRotaryPosEmbed.forward, called at patch.py:52): fp32 cos,sin [F*H*W, D/2]
  * (the reference's repeat_interleave(2) duplicates are not stored). */
