@@ -1,5 +1,5 @@
 """Launches the hot kernels in isolation at the BASELINE shapes (for `ncu --set full`): FFN-up GEMM (+GELU epilogue),
-out-proj GEMM (gated residual), dX GEMM (MN-major B), attention fwd / bwd, norm+modulate, qknorm+rope."""
+FFN-down GEMM (gated residual), dX GEMM (MN-major B), self / cross attention fwd + bwd, norm+modulate, fused q|k|v norm+rope."""
 import os
 import sys
 
@@ -27,6 +27,13 @@ delta = torch.empty(ops.attn_bwd_ws_floats(1, H, S, S), device=dev)
 qkv = rnd(R, 3 * D)
 cos = torch.randn(S, D // 2, device=dev)
 sin = torch.randn(S, D // 2, device=dev)
+L = 128
+kc, vc = rnd(1, H, L, 64), rnd(1, H, L, 64)
+dkc, dvc = torch.empty_like(kc), torch.empty_like(vc)
+biasc = torch.zeros(1, L, device=dev); biasc[:, 77:] = -10000.0
+deltac = torch.zeros(ops.attn_bwd_ws_floats(1, H, S, L), device=dev)
+q2, k2, v2 = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+dqkv = torch.empty_like(qkv)
 for _ in range(n_rep):
     ops.gemm(x, W1, f, M=R, N=4 * D, K=D, bias=b1, epi=ops.EPI_GELU, out2=pre)                       # FFN up
     ops.gemm(f, W2, h, M=R, N=D, K=4 * D, bias=b2, epi=ops.EPI_GATE_RES, res=res, gate_table=tab[5],
@@ -34,7 +41,10 @@ for _ in range(n_rep):
     ops.gemm(res, W2, f, M=R, N=4 * D, K=D, b_mn=True, epi=ops.EPI_MUL_DGELU, aux=pre)               # dX (MN-major B)
     ops.attn_fwd(q, k, v, None, ao, lse, 1, H, S, S, 0.125)
     ops.attn_bwd(q, k, v, None, ao, dout, lse, delta, dq, dk, dv, 1, H, S, S, 0.125)
+    ops.attn_fwd(q, kc, vc, biasc, ao, lse, 1, H, S, L, 0.125)                                       # cross attention
+    ops.attn_bwd(q, kc, vc, biasc, ao, dout, lse, deltac, dq, dkc, dvc, 1, H, S, L, 0.125)
     ops.norm_modulate_fwd(x, h, tab[0], temb, tab[1], temb[:, D:], 6 * D, R, D, S, 1e-6)
-    ops.qknorm_rope_fwd(qkv, 3 * D, 0, tab[0], cos, sin, q, 1, S, H, True, 1e-5)
+    ops.qkv_norm_rope_fwd(qkv, 3 * D, 0, (tab[0], tab[1], None), 0b011, cos, sin, (q2, k2, v2), 1, S, H, 1e-5)
+    ops.qkv_norm_rope_bwd((q2, k2, v2), qkv, 3 * D, 0, (tab[0], tab[1], None), 0b011, cos, sin, dqkv, 3 * D, 0, 1, S, H, 1e-5)
 torch.cuda.synchronize()
 print("done")
