@@ -164,7 +164,10 @@ def run_b200(args):
     model.prepare()
     if be is not None:
         be.apply_ddp(model)
-    step = SFTTrainStep(model, flow_weighting_scheme="logit_normal", seed=42 + rank, use_cuda_graph=not args.no_graph)
+    # optimiser settings of the reference example (examples/training/sft/ltx_video/crush_smol_lora/train.sh:88-98)
+    step = SFTTrainStep(model, flow_weighting_scheme="logit_normal", seed=42 + rank, use_cuda_graph=not args.no_graph,
+                        lr=5e-5, beta1=0.9, beta2=0.99, weight_decay=1e-4, eps=1e-8, max_grad_norm=1.0,
+                        lr_scheduler="constant_with_warmup", lr_warmup_steps=1000)
 
     # ---- synthetic data: a small pool of pinned host batches, plus one device-resident copy
     g = torch.Generator().manual_seed(1234 + rank)

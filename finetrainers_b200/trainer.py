@@ -19,6 +19,7 @@ import torch
 from . import ops
 from .model import B200LTXTransformer
 from .specification import LTXVideoModelSpecification, FlowMatchSchedulerTable
+from .lr_schedule import lr_factor_fn
 
 
 def compute_density_for_timestep_sampling(weighting_scheme: str, batch_size: int, logit_mean: float = 0.0,
@@ -78,12 +79,18 @@ class SFTTrainStep:
                  eps: float = 1e-8, max_grad_norm: float = 1.0, gradient_accumulation_steps: int = 1,
                  flow_weighting_scheme: str = "logit_normal", flow_logit_mean: float = 0.0,
                  flow_logit_std: float = 1.0, flow_mode_scale: float = 1.29, seed: int = 42,
-                 process_group=None, use_cuda_graph: bool = False):
+                 process_group=None, use_cuda_graph: bool = False, lr_scheduler: str = "constant",
+                 lr_warmup_steps: int = 0, train_steps: Optional[int] = None, lr_num_cycles: float = 1,
+                 lr_power: float = 1.0):
         self.transformer = transformer
         self.spec = spec or LTXVideoModelSpecification(transformer.cfg)
         self.scheduler = FlowMatchSchedulerTable()
         self.lr, self.beta1, self.beta2, self.wd, self.eps = lr, beta1, beta2, weight_decay, eps
         self.max_grad_norm = max_grad_norm
+        # LambdaLR semantics (finetrainers/optimizer.py:191-229): optimizer step k (1-based) runs at lr * factor(k - 1)
+        self._lr_factor = lr_factor_fn(lr_scheduler, num_warmup_steps=lr_warmup_steps, num_training_steps=train_steps,
+                                       num_cycles=lr_num_cycles, power=lr_power, lr_init=lr)
+        self.last_lr = lr * self._lr_factor(0)
         self.grad_accum = gradient_accumulation_steps
         self.scheme = flow_weighting_scheme
         self.flow_logit_mean, self.flow_logit_std, self.flow_mode_scale = flow_logit_mean, flow_logit_std, flow_mode_scale
@@ -223,8 +230,9 @@ class SFTTrainStep:
         self.metrics[0:1] = self.sumsq.sqrt()
         self.metrics[1:2] = self.loss_acc
         self.metrics[2:3] = self.loss_acc
-        ops.adamw_clip(tr.lora_flat, g, self.exp_avg, self.exp_avg_sq, g.numel(), self.sumsq, self.max_grad_norm, self.lr,
-                       self.beta1, self.beta2, self.eps, self.wd, self.opt_step, 1.0)
+        self.last_lr = self.lr * self._lr_factor(self.opt_step - 1)
+        ops.adamw_clip(tr.lora_flat, g, self.exp_avg, self.exp_avg_sq, g.numel(), self.sumsq, self.max_grad_norm,
+                       self.last_lr, self.beta1, self.beta2, self.eps, self.wd, self.opt_step, 1.0)
         self.loss_acc.zero_()
         self.micro = 0
         if not sync_metrics:

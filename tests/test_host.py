@@ -172,3 +172,21 @@ def test_lora_export_keys_and_values(tmp_path):
     assert k in sd and sd[k].shape == (128, 16) and sd[k].dtype == torch.float32
     assert torch.equal(sd[k], m.transformer_blocks[0].attn2.to_out[0].lora_B["default"].weight.detach())
     assert len(sd) == 16
+
+
+def test_lr_schedules_match_reference_lambdas():
+    """finetrainers_b200.lr_schedule against the factors the reference's own lambda functions produce
+    (tests/golden/make_lr_golden.py executes finetrainers/optimizer.py:250-432 unmodified)."""
+    import json
+    import os
+    from finetrainers_b200.lr_schedule import SCHEDULES, lr_factor_fn
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "lr_golden.json")))
+    assert {c["name"] for c in cases} == set(SCHEDULES)
+    for c in cases:
+        fn = lr_factor_fn(c["name"], **c["kwargs"])
+        for step, want in zip(c["steps"], c["factors"]):
+            assert fn(step) == want, (c["name"], c["kwargs"], step)
+    with pytest.raises(ValueError):
+        lr_factor_fn("cosine")            # needs num_training_steps
+    with pytest.raises(ValueError):
+        lr_factor_fn("nope")
