@@ -162,3 +162,56 @@ def test_cuda_graph_step_matches_eager_and_grad_accumulation():
     torch.cuda.synchronize()
     assert st.micro == 2 and gs[0].abs().max() > 0 and gs[1].abs().max() > 0
     assert torch.allclose(bm.lora_grad_flat, gs[0] + gs[1], rtol=1e-4, atol=1e-9)
+
+
+def test_three_step_trajectory_first_frame_conditioning_and_lr_schedule():
+    """Three optimizer steps of the b200 step against the oracle run the way the reference trainer runs them: first-frame
+    conditioning branch taken (base_specification.py:298-310), sigma-dependent loss weights, clip + AdamW under a
+    LambdaLR warm-up.  Per-step loss within 1e-3 (north_star); the 3-step adapter updates agree in direction and length."""
+    from finetrainers_b200.lr_schedule import lr_factor_fn
+    from finetrainers_b200.trainer import SFTTrainStep
+    O, om, bm = build_pair(SMALL, 64, seed=2)
+    st = SFTTrainStep(bm, flow_weighting_scheme="none", lr=1e-3, lr_scheduler="linear", lr_warmup_steps=2, train_steps=10, seed=11)
+    st.spec.first_frame_conditioning_p = 1.0
+    params = [p for n, p in om.named_parameters() if "lora_" in n]
+    opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.99), weight_decay=1e-4, eps=1e-8)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_factor_fn("linear", num_warmup_steps=2, num_training_steps=10))
+    p0 = {n: p.detach().clone() for n, p in om.named_parameters() if "lora_" in n}
+    for i in range(3):
+        batch = O.make_synthetic_batch(om.cfg, 2, 3, 4, 6, text_len=20, seed=300 + i)
+        cond = {"encoder_hidden_states": batch["encoder_hidden_states"].cuda(), "encoder_attention_mask": batch["encoder_attention_mask"].cuda()}
+        lat = {"latents": batch["latents"].cuda(), "latents_mean": batch["latents_mean"].cuda(), "latents_std": batch["latents_std"].cuda()}
+        st.micro_step(cond, lat, sigmas=batch["sigmas"].view(-1).cuda(), noise=batch["noise"].cuda())
+        torch.cuda.synchronize()
+        loss_b = st.loss_buf.item()
+        sig_ff = next(iter(st._static.values()))["sig_ff"].float().cpu()
+        assert (sig_ff <= 0.25 + 1e-6).all() and (sig_ff <= batch["sigmas"].view(-1) + 1e-6).all()
+        fb = {k: (v.float() if v.is_floating_point() else v) for k, v in batch.items()}
+        opt.zero_grad(set_to_none=True)
+        pred, target, sig = O.spec_forward(om, fb["latents"], fb["latents_mean"], fb["latents_std"], fb["encoder_hidden_states"],
+                                           fb["encoder_attention_mask"], fb["sigmas"], noise=fb["noise"],
+                                           first_frame_sigma=sig_ff.view(fb["sigmas"].shape))
+        loss_o = O.sft_loss(pred, target, sig)
+        loss_o.backward()
+        assert abs(loss_b - loss_o.item()) / abs(loss_o.item()) < 1e-3, (i, loss_b, loss_o.item())
+        O.clip_grad_norm_(params, 1.0)
+        assert abs(st._lr_factor(i) * 1e-3 - opt.param_groups[0]["lr"]) < 1e-12
+        opt.step()
+        sched.step()
+        st.optimizer_step()
+    torch.cuda.synchronize()
+    # Adam normalises every element to ~+-lr, so elements whose gradient is rounding noise (the cross-attention q/k
+    # adapters, see test_small_model_step_matches_oracle) move by O(lr) in either implementation; compare the UPDATE
+    # vectors of the well-conditioned adapters by direction and length instead of element-wise.
+    og = dict(om.named_parameters())
+    checked = 0
+    for n, p in bm.named_parameters():
+        if "lora_" in n and not ("attn2.to_q" in n or "attn2.to_k" in n):
+            db = (p.detach().float().cpu() - p0[n]).flatten()
+            do = (og[n].detach() - p0[n]).flatten()
+            if do.norm() == 0:
+                continue
+            cos = torch.dot(db, do) / (db.norm() * do.norm())
+            assert cos > 0.95 and abs(db.norm() / do.norm() - 1) < 0.05, (n, cos.item(), (db.norm() / do.norm()).item())
+            checked += 1
+    assert checked >= 20
