@@ -1142,14 +1142,17 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
                 mbar_wait(&mm_done[kb], (uint32_t)(((it / PP_NBUF) - 1) & 1));
                 tc_fence_after();
             }
+            const uint32_t aP = smem_u32(myP), aDS = smem_u32(myDS), aCA = smem_u32(cA), aCD = smem_u32(cD);
+            // the per-row term is only non-trivial with a key bias or a ragged X tile (DKV), resp. it carries -lse (dQ pass)
+            const bool add_row = !DKV || p.key_bias != nullptr || !row_ok;
 #pragma unroll 1
             for (int c = 0; c < TY / 32; ++c) {
                 uint32_t sv[32], dv[32];
                 tmem_ld32(tS + lane_off + c * 32, sv);
                 tmem_ld32(tDP + lane_off + c * 32, dv);
-                tmem_ld_wait();
                 float pe[32], ds[32];
                 if (no_col) {
+                    tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
                         float pp = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, rowA));
@@ -1157,25 +1160,36 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
                         ds[e] = pp * (__uint_as_float(dv[e]) - rowD);
                     }
                 } else {
+                    float ca[32], cd[32];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float4 t = lds128f(aCA + (c * 32 + u * 4) * 4);
+                        ca[u * 4] = t.x; ca[u * 4 + 1] = t.y; ca[u * 4 + 2] = t.z; ca[u * 4 + 3] = t.w;
+                        if (DKV) {
+                            const float4 d4 = lds128f(aCD + (c * 32 + u * 4) * 4);
+                            cd[u * 4] = d4.x; cd[u * 4 + 1] = d4.y; cd[u * 4 + 2] = d4.z; cd[u * 4 + 3] = d4.w;
+                        }
+                    }
+                    if (add_row) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) ca[e] += rowA;
+                    }
+                    tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
-                        const int cc = c * 32 + e;
-                        float pp = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, rowA + cA[cc]));
+                        float pp = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, ca[e]));
                         pe[e] = pp;
-                        ds[e] = pp * (__uint_as_float(dv[e]) - (DKV ? cD[cc] : rowD));
+                        ds[e] = pp * (__uint_as_float(dv[e]) - (DKV ? cd[e] : rowD));
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const uint32_t off = sw128_off(r, c * 4 + u);
-                    if (DKV) {
-                        uint4 w = make_uint4(pack_bf16x2(pe[u * 8], pe[u * 8 + 1]), pack_bf16x2(pe[u * 8 + 2], pe[u * 8 + 3]),
-                                             pack_bf16x2(pe[u * 8 + 4], pe[u * 8 + 5]), pack_bf16x2(pe[u * 8 + 6], pe[u * 8 + 7]));
-                        *reinterpret_cast<uint4*>(myP + off) = w;
-                    }
-                    uint4 w2 = make_uint4(pack_bf16x2(ds[u * 8], ds[u * 8 + 1]), pack_bf16x2(ds[u * 8 + 2], ds[u * 8 + 3]),
-                                          pack_bf16x2(ds[u * 8 + 4], ds[u * 8 + 5]), pack_bf16x2(ds[u * 8 + 6], ds[u * 8 + 7]));
-                    *reinterpret_cast<uint4*>(myDS + off) = w2;
+                    if (DKV)
+                        sts128(aP + off, pack_bf16x2(pe[u * 8], pe[u * 8 + 1]), pack_bf16x2(pe[u * 8 + 2], pe[u * 8 + 3]),
+                               pack_bf16x2(pe[u * 8 + 4], pe[u * 8 + 5]), pack_bf16x2(pe[u * 8 + 6], pe[u * 8 + 7]));
+                    sts128(aDS + off, pack_bf16x2(ds[u * 8], ds[u * 8 + 1]), pack_bf16x2(ds[u * 8 + 2], ds[u * 8 + 3]),
+                           pack_bf16x2(ds[u * 8 + 4], ds[u * 8 + 5]), pack_bf16x2(ds[u * 8 + 6], ds[u * 8 + 7]));
                 }
             }
             fence_proxy_async_smem();
