@@ -477,8 +477,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
             bool done = false;
             if (fast && j > 0) {
                 float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
-                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-                const float nm = -m_run;
+                // scale/offset FMAs and the row-sum adds run as packed fp32 pairs (FFMA2 / FADD2): this loop is issue-bound
+                uint64_t l01 = f2_pack(0.f, 0.f), l23 = l01;
+                const uint64_t nm2 = f2_pack(-m_run, -m_run), scale2 = f2_pack(p.scale_log2, p.scale_log2);
+                const uint32_t aPs = smem_u32(sP);
 #pragma unroll 1
                 for (int c = 0; c < FDB_KV / 32; ++c) {
                     uint32_t v[32];
@@ -490,21 +492,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
                         const float a0 = __uint_as_float(v[e]), a1 = __uint_as_float(v[e + 1]);
                         const float a2 = __uint_as_float(v[e + 2]), a3 = __uint_as_float(v[e + 3]);
                         t0 = fmaxf(t0, a0); t1 = fmaxf(t1, a1); t2 = fmaxf(t2, a2); t3 = fmaxf(t3, a3);
-                        pv[e] = fast_exp2(fmaf(a0, p.scale_log2, nm));
-                        pv[e + 1] = fast_exp2(fmaf(a1, p.scale_log2, nm));
-                        pv[e + 2] = fast_exp2(fmaf(a2, p.scale_log2, nm));
-                        pv[e + 3] = fast_exp2(fmaf(a3, p.scale_log2, nm));
-                        l0 += pv[e]; l1 += pv[e + 1]; l2 += pv[e + 2]; l3 += pv[e + 3];
+                        float x0, x1, x2, x3;
+                        f2_unpack(f2_fma(f2_pack(a0, a1), scale2, nm2), x0, x1);
+                        f2_unpack(f2_fma(f2_pack(a2, a3), scale2, nm2), x2, x3);
+                        pv[e] = fast_exp2(x0);
+                        pv[e + 1] = fast_exp2(x1);
+                        pv[e + 2] = fast_exp2(x2);
+                        pv[e + 3] = fast_exp2(x3);
+                        l01 = f2_add(l01, f2_pack(pv[e], pv[e + 1]));
+                        l23 = f2_add(l23, f2_pack(pv[e + 2], pv[e + 3]));
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint4 w = make_uint4(pack_bf16x2(pv[u * 8], pv[u * 8 + 1]), pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]),
-                                             pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]), pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]));
-                        *reinterpret_cast<uint4*>(sP + sw128_off(r, c * 4 + u)) = w;
-                    }
+                    for (int u = 0; u < 4; ++u)
+                        sts128(aPs + sw128_off(r, c * 4 + u), pack_bf16x2(pv[u * 8], pv[u * 8 + 1]),
+                               pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]), pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]),
+                               pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]));
                 }
                 const float mxo = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) * p.scale_log2;
                 if (!__any_sync(0xffffffffu, (mxo - m_run) > 8.0f)) {
+                    float l0, l1, l2, l3;
+                    f2_unpack(l01, l0, l1);
+                    f2_unpack(l23, l2, l3);
                     l_run += (l0 + l1) + (l2 + l3);
                     done = true;
                 }
@@ -1151,13 +1159,18 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
                 tmem_ld32(tS + lane_off + c * 32, sv);
                 tmem_ld32(tDP + lane_off + c * 32, dv);
                 float pe[32], ds[32];
+                const uint64_t scale2 = f2_pack(p.scale_log2, p.scale_log2);
                 if (no_col) {
+                    const uint64_t rowA2 = f2_pack(rowA, rowA), rowD2 = f2_pack(rowD, rowD);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        float pp = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, rowA));
-                        pe[e] = pp;
-                        ds[e] = pp * (__uint_as_float(dv[e]) - rowD);
+                    for (int e = 0; e < 32; e += 2) {
+                        float x0, x1;
+                        f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), scale2, rowA2), x0, x1);
+                        pe[e] = fast_exp2(x0);
+                        pe[e + 1] = fast_exp2(x1);
+                        const uint64_t t2 = f2_sub(f2_pack(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), rowD2);
+                        f2_unpack(f2_mul(f2_pack(pe[e], pe[e + 1]), t2), ds[e], ds[e + 1]);
                     }
                 } else {
                     float ca[32], cd[32];
@@ -1176,10 +1189,15 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
                     }
                     tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        float pp = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, ca[e]));
-                        pe[e] = pp;
-                        ds[e] = pp * (__uint_as_float(dv[e]) - (DKV ? cd[e] : rowD));
+                    for (int e = 0; e < 32; e += 2) {
+                        float x0, x1;
+                        f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), scale2,
+                                         f2_pack(ca[e], ca[e + 1])), x0, x1);
+                        pe[e] = fast_exp2(x0);
+                        pe[e + 1] = fast_exp2(x1);
+                        const uint64_t sub2 = DKV ? f2_pack(cd[e], cd[e + 1]) : f2_pack(rowD, rowD);
+                        const uint64_t t2 = f2_sub(f2_pack(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), sub2);
+                        f2_unpack(f2_mul(f2_pack(pe[e], pe[e + 1]), t2), ds[e], ds[e + 1]);
                     }
                 }
 #pragma unroll
