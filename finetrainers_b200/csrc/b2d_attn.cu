@@ -1419,36 +1419,59 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xfwd_kernel(const __grid_co
             const uint32_t par = (uint32_t)((t >> 1) & 1);
             mbar_wait(&s_full[wg], par);
             tc_fence_after();
-            // pass 1: row maximum in the log2 domain
+            // pass 1: row maximum in the log2 domain (packed fp32 pairs for the scale+bias FMAs)
+            const uint32_t aBias = smem_u32(sBias), aP = smem_u32(myP);
+            const uint64_t scale2 = f2_pack(p.scale_log2, p.scale_log2);
             float m = -INFINITY;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t sv[32];
                 tmem_ld32(tS + c * 32, sv);
+                float bb[32];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 t4 = lds128f(aBias + (c * 32 + u * 4) * 4);
+                    bb[u * 4] = t4.x; bb[u * 4 + 1] = t4.y; bb[u * 4 + 2] = t4.z; bb[u * 4 + 3] = t4.w;
+                }
                 tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) m = fmaxf(m, fmaf(__uint_as_float(sv[e]), p.scale_log2, sBias[c * 32 + e]));
+                for (int e = 0; e < 32; e += 2) {
+                    float x0, x1;
+                    f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), scale2, f2_pack(bb[e], bb[e + 1])), x0, x1);
+                    m = fmaxf(m, fmaxf(x0, x1));
+                }
             }
             const float m_use = (m == -INFINITY) ? 0.f : m;
-            float l = 0.f;
+            uint64_t l2 = f2_pack(0.f, 0.f);
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t sv[32];
                 tmem_ld32(tS + c * 32, sv);
+                float bb[32];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 t4 = lds128f(aBias + (c * 32 + u * 4) * 4);
+                    bb[u * 4] = t4.x - m_use; bb[u * 4 + 1] = t4.y - m_use; bb[u * 4 + 2] = t4.z - m_use; bb[u * 4 + 3] = t4.w - m_use;
+                }
                 tmem_ld_wait();
                 float pe[32];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    pe[e] = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, sBias[c * 32 + e]) - m_use);
-                    l += pe[e];
+                for (int e = 0; e < 32; e += 2) {
+                    float x0, x1;
+                    f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), scale2, f2_pack(bb[e], bb[e + 1])), x0, x1);
+                    pe[e] = fast_exp2(x0);
+                    pe[e + 1] = fast_exp2(x1);
+                    l2 = f2_add(l2, f2_pack(pe[e], pe[e + 1]));
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint4 w = make_uint4(pack_bf16x2(pe[u * 8], pe[u * 8 + 1]), pack_bf16x2(pe[u * 8 + 2], pe[u * 8 + 3]),
-                                         pack_bf16x2(pe[u * 8 + 4], pe[u * 8 + 5]), pack_bf16x2(pe[u * 8 + 6], pe[u * 8 + 7]));
-                    *reinterpret_cast<uint4*>(myP + (c >> 1) * X_CHUNK + sw128_off(r, (c & 1) * 4 + u)) = w;
-                }
+                for (int u = 0; u < 4; ++u)
+                    sts128(aP + (c >> 1) * X_CHUNK + sw128_off(r, (c & 1) * 4 + u), pack_bf16x2(pe[u * 8], pe[u * 8 + 1]),
+                           pack_bf16x2(pe[u * 8 + 2], pe[u * 8 + 3]), pack_bf16x2(pe[u * 8 + 4], pe[u * 8 + 5]),
+                           pack_bf16x2(pe[u * 8 + 6], pe[u * 8 + 7]));
             }
+            float l, l_hi;
+            f2_unpack(l2, l, l_hi);
+            l += l_hi;
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&p_full[wg]);
@@ -1688,7 +1711,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_co
                 const uint8_t* sdO = sQ + (t % XB_STAGES) * 2 * TILE_BYTES + TILE_BYTES;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const uint4 d4 = *reinterpret_cast<const uint4*>(sdO + sw128_off(r, u));
+                    const uint4 d4 = lds128(smem_u32(sdO) + sw128_off(r, u));
                     rowD += bf16_lo(o4[u].x) * bf16_lo(d4.x) + bf16_hi(o4[u].x) * bf16_hi(d4.x) +
                             bf16_lo(o4[u].y) * bf16_lo(d4.y) + bf16_hi(o4[u].y) * bf16_hi(d4.y) +
                             bf16_lo(o4[u].z) * bf16_lo(d4.z) + bf16_hi(o4[u].z) * bf16_hi(d4.z) +
@@ -1697,28 +1720,37 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_co
                 if (!row_ok) rowD = 0.f;
             }
             // (P/dS buffer j was last read by the MMAs of tile t-2: dq_epilogue(t-2) already waited on mm_done[j])
+            const uint32_t aP = smem_u32(myP), aDS = smem_u32(myDS), aBias = smem_u32(myBias);
+            const uint64_t scale2 = f2_pack(p.scale_log2, p.scale_log2), rowD2 = f2_pack(rowD, rowD);
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
                 uint32_t sv[32], dv[32];
                 tmem_ld32(tS + c * 32, sv);
                 tmem_ld32(tDP + c * 32, dv);
+                float bb[32];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 t4 = lds128f(aBias + (c * 32 + u * 4) * 4);
+                    bb[u * 4] = t4.x + rowA; bb[u * 4 + 1] = t4.y + rowA; bb[u * 4 + 2] = t4.z + rowA; bb[u * 4 + 3] = t4.w + rowA;
+                }
                 tmem_ld_wait();
                 float pe[32], ds[32];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const float pp = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, rowA + myBias[c * 32 + e]));
-                    pe[e] = pp;
-                    ds[e] = pp * (__uint_as_float(dv[e]) - rowD);
+                for (int e = 0; e < 32; e += 2) {
+                    float x0, x1;
+                    f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), scale2, f2_pack(bb[e], bb[e + 1])), x0, x1);
+                    pe[e] = fast_exp2(x0);
+                    pe[e + 1] = fast_exp2(x1);
+                    const uint64_t t2 = f2_sub(f2_pack(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), rowD2);
+                    f2_unpack(f2_mul(f2_pack(pe[e], pe[e + 1]), t2), ds[e], ds[e + 1]);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const uint32_t off = sw128_off(r, c * 4 + u);
-                    *reinterpret_cast<uint4*>(myP + off) =
-                        make_uint4(pack_bf16x2(pe[u * 8], pe[u * 8 + 1]), pack_bf16x2(pe[u * 8 + 2], pe[u * 8 + 3]),
-                                   pack_bf16x2(pe[u * 8 + 4], pe[u * 8 + 5]), pack_bf16x2(pe[u * 8 + 6], pe[u * 8 + 7]));
-                    *reinterpret_cast<uint4*>(myDS + off) =
-                        make_uint4(pack_bf16x2(ds[u * 8], ds[u * 8 + 1]), pack_bf16x2(ds[u * 8 + 2], ds[u * 8 + 3]),
-                                   pack_bf16x2(ds[u * 8 + 4], ds[u * 8 + 5]), pack_bf16x2(ds[u * 8 + 6], ds[u * 8 + 7]));
+                    sts128(aP + off, pack_bf16x2(pe[u * 8], pe[u * 8 + 1]), pack_bf16x2(pe[u * 8 + 2], pe[u * 8 + 3]),
+                           pack_bf16x2(pe[u * 8 + 4], pe[u * 8 + 5]), pack_bf16x2(pe[u * 8 + 6], pe[u * 8 + 7]));
+                    sts128(aDS + off, pack_bf16x2(ds[u * 8], ds[u * 8 + 1]), pack_bf16x2(ds[u * 8 + 2], ds[u * 8 + 3]),
+                           pack_bf16x2(ds[u * 8 + 4], ds[u * 8 + 5]), pack_bf16x2(ds[u * 8 + 6], ds[u * 8 + 7]));
                 }
             }
             fence_proxy_async_smem();
