@@ -83,3 +83,25 @@ def test_attention_properties_full_size():
     ops.attn_fwd(q, k[:, :, perm].contiguous(), v[:, :, perm].contiguous(), None, out2, lse2, B, H, S, S, 0.125)
     assert (out.float() - out2.float()).abs().max().item() < 2e-2
     assert (lse - lse2).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("growth", [0.02, 0.2])
+def test_attention_fwd_running_max_growth(growth):
+    """Scores that keep growing along the key axis force the online softmax through its rescale / exact two-pass path on
+    many tiles (the optimistic single pass only holds while the running maximum is stable)."""
+    from finetrainers_b200 import ops
+    torch.manual_seed(2)
+    B, H, S = 1, 4, 1024
+    q = (torch.randn(B, H, S, 64, device="cuda") * 0.3 + 1.0).bfloat16()
+    ramp = torch.arange(S, device="cuda", dtype=torch.float32).view(1, 1, S, 1) * growth / 8.0
+    k = (torch.randn(B, H, S, 64, device="cuda") * 0.3 + ramp / 64.0 * 8.0).bfloat16()   # q.k grows ~ growth per key
+    v = rnd(B, H, S, 64)
+    out = torch.zeros(B, S, H * 64, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, S, device="cuda")
+    ops.attn_fwd(q, k, v, None, out, lse, B, H, S, S, 0.125)
+    ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float(), scale=0.125)
+    ref_lse = torch.logsumexp(q.float() @ k.float().transpose(-1, -2) * 0.125, dim=-1)
+    got = out.view(B, S, H, 64).transpose(1, 2).float()
+    assert torch.isfinite(got).all()
+    assert rel_err(got, ref, 1e-2) < 2e-2
+    assert (lse - ref_lse).abs().max().item() < 2e-2
