@@ -61,6 +61,32 @@ struct GemmCfg {
 __device__ __forceinline__ void st_global_16B(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// 256-bit store (sm_100 STG.256): one full 32-byte sector per lane.  One thread owns a row here, so a warp-wide 16-byte
+// store leaves 32 half-written sectors behind; the 32-byte form halves both the store instructions and the L2 write requests.
+__device__ __forceinline__ void st_global_32B(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
+                                              uint32_t f, uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d),
+                 "r"(e), "r"(f), "r"(g), "r"(h)
+                 : "memory");
+}
+// 32 bf16 outputs of one row segment: 2 x 32 B when the segment is 32-byte aligned and complete, else 4 x 16 B (guarded)
+__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* o, const float (&v)[32], int cols_left) {
+    if (cols_left >= 32 && (reinterpret_cast<uintptr_t>(o) & 31) == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            st_global_32B(o + h * 16, pack_bf16x2(v[h * 16], v[h * 16 + 1]), pack_bf16x2(v[h * 16 + 2], v[h * 16 + 3]),
+                          pack_bf16x2(v[h * 16 + 4], v[h * 16 + 5]), pack_bf16x2(v[h * 16 + 6], v[h * 16 + 7]),
+                          pack_bf16x2(v[h * 16 + 8], v[h * 16 + 9]), pack_bf16x2(v[h * 16 + 10], v[h * 16 + 11]),
+                          pack_bf16x2(v[h * 16 + 12], v[h * 16 + 13]), pack_bf16x2(v[h * 16 + 14], v[h * 16 + 15]));
+    } else {
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8)
+            if (j8 * 8 < cols_left)
+                st_global_16B(o + j8 * 8, pack_bf16x2(v[j8 * 8], v[j8 * 8 + 1]), pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]),
+                              pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]), pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+    }
+}
+
 __device__ __forceinline__ uint4 ld_global_16B(const void* p) {
     uint4 r;
     asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -381,22 +407,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                                 }
                             }
                             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + cbase + (long long)row * p.ldc + col0;
-#pragma unroll
-                            for (int j8 = 0; j8 < 4; ++j8)
-                                if (col0 + j8 * 8 < p.N)
-                                    st_global_16B(o + j8 * 8, pack_bf16x2(v[j8 * 8], v[j8 * 8 + 1]),
-                                                  pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]),
-                                                  pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]),
-                                                  pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+                            store_row32_bf16(o, v, p.N - col0);
                             if (has2) {
                                 __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + cbase + (long long)row * p.ldc2 + col0;
-#pragma unroll
-                                for (int j8 = 0; j8 < 4; ++j8)
-                                    if (col0 + j8 * 8 < p.N)
-                                        st_global_16B(o2 + j8 * 8, pack_bf16x2(v2[j8 * 8], v2[j8 * 8 + 1]),
-                                                      pack_bf16x2(v2[j8 * 8 + 2], v2[j8 * 8 + 3]),
-                                                      pack_bf16x2(v2[j8 * 8 + 4], v2[j8 * 8 + 5]),
-                                                      pack_bf16x2(v2[j8 * 8 + 6], v2[j8 * 8 + 7]));
+                                store_row32_bf16(o2, v2, p.N - col0);
                             }
                         }
                     }
