@@ -327,14 +327,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
             if (qrow < p.Sq) {
                 __nv_bfloat16* o = p.out + ((long long)b * p.Sq + qrow) * (p.H * HD) + h * HD + c * 32;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint4 w = make_uint4(
-                        pack_bf16x2(__uint_as_float(v[u * 8]) * inv_l, __uint_as_float(v[u * 8 + 1]) * inv_l),
-                        pack_bf16x2(__uint_as_float(v[u * 8 + 2]) * inv_l, __uint_as_float(v[u * 8 + 3]) * inv_l),
-                        pack_bf16x2(__uint_as_float(v[u * 8 + 4]) * inv_l, __uint_as_float(v[u * 8 + 5]) * inv_l),
-                        pack_bf16x2(__uint_as_float(v[u * 8 + 6]) * inv_l, __uint_as_float(v[u * 8 + 7]) * inv_l));
-                    *reinterpret_cast<uint4*>(o + u * 8) = w;
-                }
+                for (int u = 0; u < 2; ++u)  // 2 x 32 B: one full sector per lane and store
+                    st_global_32B(o + u * 16,
+                                  pack_bf16x2(__uint_as_float(v[u * 16]) * inv_l, __uint_as_float(v[u * 16 + 1]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v[u * 16 + 2]) * inv_l, __uint_as_float(v[u * 16 + 3]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v[u * 16 + 4]) * inv_l, __uint_as_float(v[u * 16 + 5]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v[u * 16 + 6]) * inv_l, __uint_as_float(v[u * 16 + 7]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v[u * 16 + 8]) * inv_l, __uint_as_float(v[u * 16 + 9]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v[u * 16 + 10]) * inv_l, __uint_as_float(v[u * 16 + 11]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v[u * 16 + 12]) * inv_l, __uint_as_float(v[u * 16 + 13]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v[u * 16 + 14]) * inv_l, __uint_as_float(v[u * 16 + 15]) * inv_l));
             }
         }
         if (qrow < p.Sq) p.lse[((long long)b * p.H + h) * p.Sq + qrow] = m_run * LN2 + logf(l_run);
@@ -601,14 +603,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
             if (qrow < p.Sq) {
                 __nv_bfloat16* o = p.out + ((long long)b * p.Sq + qrow) * (p.H * HD) + h * HD + c * 32;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint4 w = make_uint4(
-                        pack_bf16x2(__uint_as_float(v[u * 8]) * inv_l, __uint_as_float(v[u * 8 + 1]) * inv_l),
-                        pack_bf16x2(__uint_as_float(v[u * 8 + 2]) * inv_l, __uint_as_float(v[u * 8 + 3]) * inv_l),
-                        pack_bf16x2(__uint_as_float(v[u * 8 + 4]) * inv_l, __uint_as_float(v[u * 8 + 5]) * inv_l),
-                        pack_bf16x2(__uint_as_float(v[u * 8 + 6]) * inv_l, __uint_as_float(v[u * 8 + 7]) * inv_l));
-                    *reinterpret_cast<uint4*>(o + u * 8) = w;
-                }
+                for (int u = 0; u < 2; ++u)  // 2 x 32 B: one full sector per lane and store
+                    st_global_32B(o + u * 16,
+                                  pack_bf16x2(__uint_as_float(v[u * 16]) * inv_l, __uint_as_float(v[u * 16 + 1]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v[u * 16 + 2]) * inv_l, __uint_as_float(v[u * 16 + 3]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v[u * 16 + 4]) * inv_l, __uint_as_float(v[u * 16 + 5]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v[u * 16 + 6]) * inv_l, __uint_as_float(v[u * 16 + 7]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v[u * 16 + 8]) * inv_l, __uint_as_float(v[u * 16 + 9]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v[u * 16 + 10]) * inv_l, __uint_as_float(v[u * 16 + 11]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v[u * 16 + 12]) * inv_l, __uint_as_float(v[u * 16 + 13]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v[u * 16 + 14]) * inv_l, __uint_as_float(v[u * 16 + 15]) * inv_l));
             }
         }
         if (qrow < p.Sq) p.lse[((long long)b * p.H + h) * p.Sq + qrow] = m_run * LN2 + logf(l_run);
@@ -1489,14 +1493,16 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xfwd_kernel(const __grid_co
                 if (qrow < p.Sq) {
                     __nv_bfloat16* o = p.out + ((long long)b * p.Sq + qrow) * (p.H * HD) + h * HD + c * 32;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint4 w = make_uint4(
-                            pack_bf16x2(__uint_as_float(v[u * 8]) * inv_l, __uint_as_float(v[u * 8 + 1]) * inv_l),
-                            pack_bf16x2(__uint_as_float(v[u * 8 + 2]) * inv_l, __uint_as_float(v[u * 8 + 3]) * inv_l),
-                            pack_bf16x2(__uint_as_float(v[u * 8 + 4]) * inv_l, __uint_as_float(v[u * 8 + 5]) * inv_l),
-                            pack_bf16x2(__uint_as_float(v[u * 8 + 6]) * inv_l, __uint_as_float(v[u * 8 + 7]) * inv_l));
-                        *reinterpret_cast<uint4*>(o + u * 8) = w;
-                    }
+                    for (int u = 0; u < 2; ++u)
+                        st_global_32B(o + u * 16,
+                                      pack_bf16x2(__uint_as_float(v[u * 16]) * inv_l, __uint_as_float(v[u * 16 + 1]) * inv_l),
+                                      pack_bf16x2(__uint_as_float(v[u * 16 + 2]) * inv_l, __uint_as_float(v[u * 16 + 3]) * inv_l),
+                                      pack_bf16x2(__uint_as_float(v[u * 16 + 4]) * inv_l, __uint_as_float(v[u * 16 + 5]) * inv_l),
+                                      pack_bf16x2(__uint_as_float(v[u * 16 + 6]) * inv_l, __uint_as_float(v[u * 16 + 7]) * inv_l),
+                                      pack_bf16x2(__uint_as_float(v[u * 16 + 8]) * inv_l, __uint_as_float(v[u * 16 + 9]) * inv_l),
+                                      pack_bf16x2(__uint_as_float(v[u * 16 + 10]) * inv_l, __uint_as_float(v[u * 16 + 11]) * inv_l),
+                                      pack_bf16x2(__uint_as_float(v[u * 16 + 12]) * inv_l, __uint_as_float(v[u * 16 + 13]) * inv_l),
+                                      pack_bf16x2(__uint_as_float(v[u * 16 + 14]) * inv_l, __uint_as_float(v[u * 16 + 15]) * inv_l));
                 }
             }
             tc_fence_before();  // O[wg] / S[wg] reads are ordered before this warpgroup's next p_full arrival
@@ -1890,6 +1896,7 @@ extern "C" int b2d_attn_fwd(const void* q, const void* k, const void* v, const f
                             int32_t B, int32_t H, int32_t Sq, int32_t Sk, float scale, void* stream) {
     B2D_BIND(q);
     if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) return set_error(B2D_ERR_SHAPE, "attn_fwd: bad dims");
+    if (reinterpret_cast<uintptr_t>(out) & 31) return set_error(B2D_ERR_ALIGN, "attn_fwd: out must be 32-byte aligned");
     AttnFwdParams p;
     memset(&p, 0, sizeof(p));
     int rc;

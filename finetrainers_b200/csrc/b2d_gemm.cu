@@ -61,14 +61,6 @@ struct GemmCfg {
 __device__ __forceinline__ void st_global_16B(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// 256-bit store (sm_100 STG.256): one full 32-byte sector per lane.  One thread owns a row here, so a warp-wide 16-byte
-// store leaves 32 half-written sectors behind; the 32-byte form halves both the store instructions and the L2 write requests.
-__device__ __forceinline__ void st_global_32B(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
-                                              uint32_t f, uint32_t g, uint32_t h) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d),
-                 "r"(e), "r"(f), "r"(g), "r"(h)
-                 : "memory");
-}
 // 32 bf16 outputs of one row segment: 2 x 32 B when the segment is 32-byte aligned and complete, else 4 x 16 B (guarded)
 __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* o, const float (&v)[32], int cols_left) {
     if (cols_left >= 32 && (reinterpret_cast<uintptr_t>(o) & 31) == 0) {
@@ -279,9 +271,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             auto prefetch = [&](int c) {
                 if (side_row != nullptr && row_ok) {
                     const int col0 = n0 + c * 32;
+                    const __nv_bfloat16* sp = side_row + col0;
+                    if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(sp) & 31) == 0) {  // 2 x 32 B: full sectors per lane
+                        ld_global_32B(sp, pf[0], pf[1]);
+                        ld_global_32B(sp + 16, pf[2], pf[3]);
+                    } else {
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8)
-                        if (col0 + j8 * 8 < p.N) pf[j8] = ld_global_16B(side_row + col0 + j8 * 8);
+                        for (int j8 = 0; j8 < 4; ++j8)
+                            if (col0 + j8 * 8 < p.N) pf[j8] = ld_global_16B(sp + j8 * 8);
+                    }
                 }
             };
             prefetch(c_begin);

@@ -153,6 +153,20 @@ __device__ __forceinline__ void griddep_launch_dependents() {
 }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// 256-bit store (sm_100 STG.256): one full 32-byte sector per lane.  One thread owns a row here, so a warp-wide 16-byte
+// store leaves 32 half-written sectors behind; the 32-byte form halves both the store instructions and the L2 write requests.
+__device__ __forceinline__ void st_global_32B(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
+                                              uint32_t f, uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d),
+                 "r"(e), "r"(f), "r"(g), "r"(h)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_32B(const void* p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
+
 // packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: one issue slot for two lanes' worth of fp32 math).  The softmax /
 // dS loops of the attention kernels are issue-bound, not FP32-pipe-bound, so halving the instruction count of their
 // multiply-add chains is a direct win.  Pairs live in 64-bit registers; pack/unpack are register renames when adjacent.
