@@ -481,7 +481,8 @@ def sft_loss(pred, target, sigmas, scheme: str = "none"):
 
 
 def clip_grad_norm_(params, max_norm: float):
-    """utils/torch.py:99-161 (L2, foreach semantics)."""
+    """utils/torch.py:99-161 (L2, foreach semantics).  Pinned against the reference's own function by
+    tests/golden/clip_golden.pt (tests/test_oracle_golden.py::test_clip_grad_norm_golden)."""
     grads = [p.grad for p in params if p.grad is not None]
     total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g.float(), 2.0) for g in grads]), 2.0)
     coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)

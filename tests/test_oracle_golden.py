@@ -95,3 +95,20 @@ def test_oracle_fqn_tree():
         assert k in names, k
     # LoRA params: 8 adapted linears / block, 2 tensors each
     assert sum("lora_" in n for n in names) == 16
+
+
+def test_clip_grad_norm_golden():
+    """oracle.clip_grad_norm_ against gradients clipped by the reference's own clip_grad_norm_ / _get_total_norm /
+    _clip_grads_with_norm_ (finetrainers/utils/torch.py:99-161,299-381, executed unmodified by make_clip_golden.py)."""
+    import os
+    from oracle import ltx_oracle as O
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "clip_golden.pt"), weights_only=True)
+    for tag in ("big", "small"):
+        params = [torch.nn.Parameter(torch.zeros_like(x)) for x in g[f"{tag}_grads_in"]]
+        for p, x in zip(params, g[f"{tag}_grads_in"]):
+            p.grad = x.clone()
+        total = O.clip_grad_norm_(params, 1.0)
+        assert torch.allclose(total, g[f"{tag}_total_norm"], rtol=1e-6, atol=0)
+        for p, want in zip(params, g[f"{tag}_grads_out"]):
+            assert torch.allclose(p.grad, want, rtol=1e-6, atol=1e-12)
+    assert g["big_total_norm"] > 1.0 > g["small_total_norm"]      # one case clips, the other passes through
