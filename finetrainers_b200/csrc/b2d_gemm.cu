@@ -85,6 +85,169 @@ __device__ __forceinline__ uint4 ld_global_16B(const void* p) {
     return r;
 }
 
+// Epilogue of one output tile for one thread (= one accumulator row): TMEM -> registers -> fused epilogue -> global.
+// Shared by the 1-CTA and the CTA-pair kernel (each CTA of a pair owns 128 rows of the 256-row pair tile).
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmKParams& p, int mt, int nt, int z, int q, int lane,
+                                                   uint32_t tmem_base, int acc, uint32_t acc_phase, uint64_t* tfull_bar,
+                                                   int c_begin, int c_end, int epi, const __nv_bfloat16* side,
+                                                   long long ldside) {
+    const int row = mt * BLOCK_M + q * 32 + lane;
+    const int n0 = nt * BN;
+    const bool row_ok = row < p.M;
+    const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+    const int b = (p.rows_per_sample > 0) ? (row_ok ? row / p.rows_per_sample : 0) : 0;
+    const long long cbase = (long long)z * p.c_boff;
+    const __nv_bfloat16* side_row = side ? side + (long long)row * ldside : nullptr;
+    uint4 pf[4];
+    auto prefetch = [&](int c) {
+        if (side_row != nullptr && row_ok) {
+            const int col0 = n0 + c * 32;
+            const __nv_bfloat16* sp = side_row + col0;
+            if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(sp) & 31) == 0) {  // 2 x 32 B: full sectors per lane
+                ld_global_32B(sp, pf[0], pf[1]);
+                ld_global_32B(sp + 16, pf[2], pf[3]);
+            } else {
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8)
+                    if (col0 + j8 * 8 < p.N) pf[j8] = ld_global_16B(sp + j8 * 8);
+            }
+        }
+    };
+    prefetch(c_begin);
+    mbar_wait(&tfull_bar[acc], acc_phase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; ++c) {
+        uint4 cur[4] = {pf[0], pf[1], pf[2], pf[3]};
+        if (c + 1 < c_end) prefetch(c + 1);
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row_ok && col0 < p.N) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+            if (epi == B2D_EPI_F32_ATOMIC) {
+                float* o = reinterpret_cast<float*>(p.out) + cbase + (long long)row * p.ldc + col0;
+                // one thread owns a row, so a warp-wide scalar atomic touches 32 lines: use 16-byte vector atomics
+                // (4x fewer L2 transactions) whenever the row segment is 16-byte aligned
+                const bool vec_ok = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    if (vec_ok && col0 + j4 * 4 + 3 < p.N) {
+                        atomicAdd(reinterpret_cast<float4*>(o + j4 * 4),
+                                  make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = j4 * 4; j < j4 * 4 + 4; ++j)
+                            if (col0 + j < p.N) atomicAdd(o + j, v[j]);
+                    }
+                }
+            } else if (epi == B2D_EPI_F32_ATOMIC_T) {
+                float* o = reinterpret_cast<float*>(p.out) + cbase + row;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < p.N) atomicAdd(o + (long long)(col0 + j) * p.ldc, v[j]);
+            } else {
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        if (col0 + j8 * 8 < p.N) {
+                            uint4 bb = ld_global_16B(p.bias + (long long)z * p.bias_boff + col0 + j8 * 8);
+                            const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[j8 * 8 + 2 * e] += bf16_lo(bw[e]);
+                                v[j8 * 8 + 2 * e + 1] += bf16_hi(bw[e]);
+                            }
+                        }
+                    }
+                }
+                if (epi == B2D_EPI_F32_STORE) {
+                    float* o = reinterpret_cast<float*>(p.out) + cbase + (long long)row * p.ldc + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (col0 + j < p.N)
+                            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+                    float v2[32];
+                    bool has2 = false;
+                    if (epi == B2D_EPI_GELU || epi == B2D_EPI_SILU) {
+                        has2 = p.out2 != nullptr;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            v2[j] = v[j];
+                            v[j] = (epi == B2D_EPI_GELU) ? gelu_tanh(v[j]) : silu(v[j]);
+                        }
+                    } else if (epi == B2D_EPI_GATE_RES) {
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            if (col0 + j8 * 8 < p.N) {
+                                const uint32_t rw[4] = {cur[j8].x, cur[j8].y, cur[j8].z, cur[j8].w};
+                                float g[8];
+                                if (p.gate_table != nullptr) {
+                                    uint4 gt = ld_global_16B(p.gate_table + col0 + j8 * 8);
+                                    uint4 ge = ld_global_16B(p.gate_temb + (long long)b * p.temb_stride + col0 + j8 * 8);
+                                    const uint32_t gtw[4] = {gt.x, gt.y, gt.z, gt.w};
+                                    const uint32_t gew[4] = {ge.x, ge.y, ge.z, ge.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        g[2 * e] = bf16_lo(gtw[e]) + bf16_lo(gew[e]);
+                                        g[2 * e + 1] = bf16_hi(gtw[e]) + bf16_hi(gew[e]);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) g[e] = 1.f;
+                                }
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    v[j8 * 8 + 2 * e] = bf16_lo(rw[e]) + g[2 * e] * v[j8 * 8 + 2 * e];
+                                    v[j8 * 8 + 2 * e + 1] = bf16_hi(rw[e]) + g[2 * e + 1] * v[j8 * 8 + 2 * e + 1];
+                                }
+                                if (p.gate2_table != nullptr && p.out2 != nullptr) {
+                                    uint4 gt = ld_global_16B(p.gate2_table + col0 + j8 * 8);
+                                    uint4 ge = ld_global_16B(p.gate2_temb + (long long)b * p.temb_stride + col0 + j8 * 8);
+                                    const uint32_t gtw[4] = {gt.x, gt.y, gt.z, gt.w};
+                                    const uint32_t gew[4] = {ge.x, ge.y, ge.z, ge.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        // the bf16-rounded primary output is what the next op sees
+                                        float a0 = __bfloat162float(__float2bfloat16_rn(v[j8 * 8 + 2 * e]));
+                                        float a1 = __bfloat162float(__float2bfloat16_rn(v[j8 * 8 + 2 * e + 1]));
+                                        v2[j8 * 8 + 2 * e] = a0 * (bf16_lo(gtw[e]) + bf16_lo(gew[e]));
+                                        v2[j8 * 8 + 2 * e + 1] = a1 * (bf16_hi(gtw[e]) + bf16_hi(gew[e]));
+                                    }
+                                }
+                            }
+                        }
+                        has2 = (p.gate2_table != nullptr && p.out2 != nullptr);
+                    } else if (epi == B2D_EPI_MUL_DGELU) {
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            if (col0 + j8 * 8 < p.N) {
+                                const uint32_t aw[4] = {cur[j8].x, cur[j8].y, cur[j8].z, cur[j8].w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    v[j8 * 8 + 2 * e] *= dgelu_tanh(bf16_lo(aw[e]));
+                                    v[j8 * 8 + 2 * e + 1] *= dgelu_tanh(bf16_hi(aw[e]));
+                                }
+                            }
+                        }
+                    }
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + cbase + (long long)row * p.ldc + col0;
+                    store_row32_bf16(o, v, p.N - col0);
+                    if (has2) {
+                        __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + cbase + (long long)row * p.ldc2 + col0;
+                        store_row32_bf16(o2, v2, p.N - col0);
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmKParams p) {
     griddep_launch_dependents();
@@ -260,160 +423,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             int nt = t % p.n_tiles;
             t /= p.n_tiles;
             int z = t / p.splits;
-            const int row = mt * BLOCK_M + q * 32 + lane;
-            const int n0 = nt * BN;
-            const bool row_ok = row < p.M;
-            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-            const int b = (p.rows_per_sample > 0) ? (row_ok ? row / p.rows_per_sample : 0) : 0;
-            const long long cbase = (long long)z * p.c_boff;
-            const __nv_bfloat16* side_row = side ? side + (long long)row * ldside : nullptr;
-            uint4 pf[4];
-            auto prefetch = [&](int c) {
-                if (side_row != nullptr && row_ok) {
-                    const int col0 = n0 + c * 32;
-                    const __nv_bfloat16* sp = side_row + col0;
-                    if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(sp) & 31) == 0) {  // 2 x 32 B: full sectors per lane
-                        ld_global_32B(sp, pf[0], pf[1]);
-                        ld_global_32B(sp + 16, pf[2], pf[3]);
-                    } else {
-#pragma unroll
-                        for (int j8 = 0; j8 < 4; ++j8)
-                            if (col0 + j8 * 8 < p.N) pf[j8] = ld_global_16B(sp + j8 * 8);
-                    }
-                }
-            };
-            prefetch(c_begin);
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = c_begin; c < c_end; ++c) {
-                uint4 cur[4] = {pf[0], pf[1], pf[2], pf[3]};
-                if (c + 1 < c_end) prefetch(c + 1);
-                uint32_t r[32];
-                tmem_ld32(taddr + c * 32, r);
-                tmem_ld_wait();
-                const int col0 = n0 + c * 32;
-                if (row_ok && col0 < p.N) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-                    if (epi == B2D_EPI_F32_ATOMIC) {
-                        float* o = reinterpret_cast<float*>(p.out) + cbase + (long long)row * p.ldc + col0;
-                        // one thread owns a row, so a warp-wide scalar atomic touches 32 lines: use 16-byte vector atomics
-                        // (4x fewer L2 transactions) whenever the row segment is 16-byte aligned
-                        const bool vec_ok = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            if (vec_ok && col0 + j4 * 4 + 3 < p.N) {
-                                atomicAdd(reinterpret_cast<float4*>(o + j4 * 4),
-                                          make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]));
-                            } else {
-#pragma unroll
-                                for (int j = j4 * 4; j < j4 * 4 + 4; ++j)
-                                    if (col0 + j < p.N) atomicAdd(o + j, v[j]);
-                            }
-                        }
-                    } else if (epi == B2D_EPI_F32_ATOMIC_T) {
-                        float* o = reinterpret_cast<float*>(p.out) + cbase + row;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.N) atomicAdd(o + (long long)(col0 + j) * p.ldc, v[j]);
-                    } else {
-                        if (p.bias != nullptr) {
-#pragma unroll
-                            for (int j8 = 0; j8 < 4; ++j8) {
-                                if (col0 + j8 * 8 < p.N) {
-                                    uint4 bb = ld_global_16B(p.bias + (long long)z * p.bias_boff + col0 + j8 * 8);
-                                    const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        v[j8 * 8 + 2 * e] += bf16_lo(bw[e]);
-                                        v[j8 * 8 + 2 * e + 1] += bf16_hi(bw[e]);
-                                    }
-                                }
-                            }
-                        }
-                        if (epi == B2D_EPI_F32_STORE) {
-                            float* o = reinterpret_cast<float*>(p.out) + cbase + (long long)row * p.ldc + col0;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                if (col0 + j < p.N)
-                                    *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        } else {
-                            float v2[32];
-                            bool has2 = false;
-                            if (epi == B2D_EPI_GELU || epi == B2D_EPI_SILU) {
-                                has2 = p.out2 != nullptr;
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    v2[j] = v[j];
-                                    v[j] = (epi == B2D_EPI_GELU) ? gelu_tanh(v[j]) : silu(v[j]);
-                                }
-                            } else if (epi == B2D_EPI_GATE_RES) {
-#pragma unroll
-                                for (int j8 = 0; j8 < 4; ++j8) {
-                                    if (col0 + j8 * 8 < p.N) {
-                                        const uint32_t rw[4] = {cur[j8].x, cur[j8].y, cur[j8].z, cur[j8].w};
-                                        float g[8];
-                                        if (p.gate_table != nullptr) {
-                                            uint4 gt = ld_global_16B(p.gate_table + col0 + j8 * 8);
-                                            uint4 ge = ld_global_16B(p.gate_temb + (long long)b * p.temb_stride + col0 + j8 * 8);
-                                            const uint32_t gtw[4] = {gt.x, gt.y, gt.z, gt.w};
-                                            const uint32_t gew[4] = {ge.x, ge.y, ge.z, ge.w};
-#pragma unroll
-                                            for (int e = 0; e < 4; ++e) {
-                                                g[2 * e] = bf16_lo(gtw[e]) + bf16_lo(gew[e]);
-                                                g[2 * e + 1] = bf16_hi(gtw[e]) + bf16_hi(gew[e]);
-                                            }
-                                        } else {
-#pragma unroll
-                                            for (int e = 0; e < 8; ++e) g[e] = 1.f;
-                                        }
-#pragma unroll
-                                        for (int e = 0; e < 4; ++e) {
-                                            v[j8 * 8 + 2 * e] = bf16_lo(rw[e]) + g[2 * e] * v[j8 * 8 + 2 * e];
-                                            v[j8 * 8 + 2 * e + 1] = bf16_hi(rw[e]) + g[2 * e + 1] * v[j8 * 8 + 2 * e + 1];
-                                        }
-                                        if (p.gate2_table != nullptr && p.out2 != nullptr) {
-                                            uint4 gt = ld_global_16B(p.gate2_table + col0 + j8 * 8);
-                                            uint4 ge = ld_global_16B(p.gate2_temb + (long long)b * p.temb_stride + col0 + j8 * 8);
-                                            const uint32_t gtw[4] = {gt.x, gt.y, gt.z, gt.w};
-                                            const uint32_t gew[4] = {ge.x, ge.y, ge.z, ge.w};
-#pragma unroll
-                                            for (int e = 0; e < 4; ++e) {
-                                                // the bf16-rounded primary output is what the next op sees
-                                                float a0 = __bfloat162float(__float2bfloat16_rn(v[j8 * 8 + 2 * e]));
-                                                float a1 = __bfloat162float(__float2bfloat16_rn(v[j8 * 8 + 2 * e + 1]));
-                                                v2[j8 * 8 + 2 * e] = a0 * (bf16_lo(gtw[e]) + bf16_lo(gew[e]));
-                                                v2[j8 * 8 + 2 * e + 1] = a1 * (bf16_hi(gtw[e]) + bf16_hi(gew[e]));
-                                            }
-                                        }
-                                    }
-                                }
-                                has2 = (p.gate2_table != nullptr && p.out2 != nullptr);
-                            } else if (epi == B2D_EPI_MUL_DGELU) {
-#pragma unroll
-                                for (int j8 = 0; j8 < 4; ++j8) {
-                                    if (col0 + j8 * 8 < p.N) {
-                                        const uint32_t aw[4] = {cur[j8].x, cur[j8].y, cur[j8].z, cur[j8].w};
-#pragma unroll
-                                        for (int e = 0; e < 4; ++e) {
-                                            v[j8 * 8 + 2 * e] *= dgelu_tanh(bf16_lo(aw[e]));
-                                            v[j8 * 8 + 2 * e + 1] *= dgelu_tanh(bf16_hi(aw[e]));
-                                        }
-                                    }
-                                }
-                            }
-                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + cbase + (long long)row * p.ldc + col0;
-                            store_row32_bf16(o, v, p.N - col0);
-                            if (has2) {
-                                __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + cbase + (long long)row * p.ldc2 + col0;
-                                store_row32_bf16(o2, v2, p.N - col0);
-                            }
-                        }
-                    }
-                }
-            }
+            gemm_epilogue_tile<BN>(p, mt, nt, z, q, lane, tmem_base, acc, acc_phase, tfull_bar, c_begin, c_end, epi, side,
+                                   ldside);
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) {
