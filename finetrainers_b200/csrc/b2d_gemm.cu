@@ -442,6 +442,192 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
 }
 
+// ================================================================================================
+// CTA-pair variant (EXPERIMENTAL, opt-in with B2D_GEMM_2CTA=1; not yet run on hardware - see DESIGN.md section 9).
+// The 1-CTA kernel above is bound by operand delivery: every SM ingests a full 256-row B tile per k-block.  Here two CTAs
+// of a 2-CTA cluster share one 256 x 256 tile: each stages its own 128 rows of A and its own 128 rows (half) of B, the
+// pair's leader issues one tcgen05.mma.cta_group::2 (M = 256) that reads both halves, and each CTA's TMEM receives its
+// 128 accumulator rows - per-SM ingest per k-block drops from 48 KB to 32 KB.  A is K-major, BN = 256, no split-K.
+//   barriers: full (leader only; both CTAs' TMA loads credit it) / empty (one multicast commit arrival in each CTA) /
+//             tmem-full (multicast commit) / tmem-empty (leader only; 256 + 256 arrivals, the peer's arrive remotely)
+// ================================================================================================
+template <int B_MN>
+struct Gemm2Cfg {
+    static constexpr int BN = 256;
+    static constexpr int B_STAGE_BYTES = (BN / 2) * BLOCK_K * 2;   // this CTA's half of B: 16 KB in either majorness
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = 6;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm2_kernel(const __grid_constant__ GemmKParams p) {
+    using Cfg = Gemm2Cfg<B_MN>;
+    constexpr int BN = Cfg::BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + Cfg::STAGES;
+    uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+        if (p.K2 > 0) {
+            tma_prefetch_desc(&p.tmA2);
+            tma_prefetch_desc(&p.tmB2);
+        }
+        for (int i = 0; i < Cfg::STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 2 * 256);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    __syncwarp();
+    cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / credited TMA
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int m_pairs = (p.m_tiles + 1) / 2;
+    const int total = m_pairs * p.n_tiles * p.batch;
+    const int n_clusters = gridDim.x / 2, cid = blockIdx.x / 2;
+    const int nkb = p.kb_main + p.kb_ext;
+
+    if (warp == 0) {
+        // ============================== TMA producer (both CTAs) ==============================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = cid; w < total; w += n_clusters) {
+                const int mp = w % m_pairs;
+                const int t = w / m_pairs;
+                const int nt = t % p.n_tiles, z = t / p.n_tiles;
+                const int m0 = (2 * mp + rank) * BLOCK_M;          // this CTA's 128 rows of the 256-row pair tile
+                const int n0t = nt * BN, n0 = n0t + rank * (BN / 2);  // this CTA's half of the B tile
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sB = sA + A_STAGE_BYTES;
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes land here
+                    if (i < p.kb_main) {
+                        const int k0 = i * BLOCK_K;
+                        tma_load_2d_2sm(sA, &p.tmA, &full_bar[stage], k0 + z * p.a_bcol, m0 + z * p.a_brow);
+                        if (B_MN == 0) {
+                            tma_load_2d_2sm(sB, &p.tmB, &full_bar[stage], k0 + z * p.b_bcol, n0 + z * p.b_brow);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BN / 128; ++j)
+                                tma_load_2d_2sm(sB + j * 8192, &p.tmB, &full_bar[stage], n0 + 64 * j + z * p.b_bcol,
+                                                k0 + z * p.b_brow);
+                        }
+                    } else {
+                        const int k2 = (i - p.kb_main) * BLOCK_K;
+                        const int a2off = p.a2_group_n > 0 ? (n0t / p.a2_group_n) * p.K2 : 0;
+                        tma_load_2d_2sm(sA, &p.tmA2, &full_bar[stage], k2 + a2off, m0 + z * p.a2_brow);
+                        if (B_MN == 0) {
+                            tma_load_2d_2sm(sB, &p.tmB2, &full_bar[stage], k2, n0 + z * p.b2_brow);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BN / 128; ++j)
+                                tma_load_2d_2sm(sB + j * 8192, &p.tmB2, &full_bar[stage], n0 + 64 * j, k2 + z * p.b2_brow);
+                        }
+                    }
+                    if (++stage == Cfg::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer (leader CTA only) ==============================
+        if (leader && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BN, 0, B_MN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int w = cid; w < total; w += n_clusters) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sB = sA + A_STAGE_BYTES;
+                    const uint32_t alo = sdesc_lo_kmajor(sA);
+                    const uint32_t blo = (B_MN != 0) ? sdesc_lo_mnmajor(sB) : sdesc_lo_kmajor(sB);
+                    constexpr uint32_t bstep = (B_MN != 0) ? SDESC_KSTEP_MNMAJOR : SDESC_KSTEP_KMAJOR;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k)
+                        umma_f16_lo_2sm(tmem_d, alo + k * SDESC_KSTEP_KMAJOR, blo + k * bstep, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_2sm_mc(&empty_bar[stage], 0x3);  // frees the stage in BOTH CTAs
+                    if (++stage == Cfg::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit_2sm_mc(&tfull_bar[acc], 0x3);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ============================== epilogue warps (both CTAs, own 128 rows) ==============================
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int NCH = BN / 32;
+        const int c_begin = half ? (NCH + 1) / 2 : 0;
+        const int c_end = half ? NCH : (NCH + 1) / 2;
+        const int epi = p.epi;
+        const __nv_bfloat16* side = (epi == B2D_EPI_GATE_RES) ? p.res : ((epi == B2D_EPI_MUL_DGELU) ? p.aux : nullptr);
+        const long long ldside = (epi == B2D_EPI_GATE_RES) ? p.ldres : p.ldaux;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = cid; w < total; w += n_clusters) {
+            const int mp = w % m_pairs;
+            const int t = w / m_pairs;
+            const int nt = t % p.n_tiles, z = t / p.n_tiles;
+            gemm_epilogue_tile<BN>(p, 2 * mp + rank, nt, z, q, lane, tmem_base, acc, acc_phase, tfull_bar, c_begin, c_end, epi,
+                                   side, ldside);
+            tc_fence_before();
+            mbar_arrive_leader(&tempty_bar[acc]);  // the MMA issuer lives in the leader CTA
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncwarp();
+    cluster_sync_all();  // nobody frees TMEM / exits while the peer may still read its smem or signal its barriers
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -460,6 +646,24 @@ static int launch_gemm(const GemmKParams& kp, int grid, cudaStream_t stream) {
     launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, kp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
+    return B2D_OK;
+}
+
+template <int B_MN>
+static int launch_gemm2(const GemmKParams& kp, int clusters, cudaStream_t stream) {
+    using Cfg = Gemm2Cfg<B_MN>;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto kern = gemm2_kernel<B_MN>;
+    if (dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "cudaFuncSetAttribute(gemm2): %s", cudaGetErrorString(e));
+        attr_set[dev] = true;
+    }
+    launch_kc(kern, dim3(2 * clusters), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, 2, kp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "gemm2 launch: %s", cudaGetErrorString(e));
     return B2D_OK;
 }
 
@@ -537,6 +741,11 @@ extern "C" int b2d_gemm(const b2d_gemm_desc* d, void* stream_v) {
     if (d->a2_group_n > 0 && (d->a2_group_n % bn) != 0)
         return set_error(B2D_ERR_ARG, "gemm: a2_group_n (%d) must be a multiple of block_n (%d)", d->a2_group_n, bn);
 
+    // CTA-pair kernel (experimental, opt-in): 256-wide tiles of a K-major-A GEMM with at least one full pair of M tiles
+    static const bool two_cta_on = []() { const char* e = getenv("B2D_GEMM_2CTA"); return e && e[0] == '1'; }();
+    const bool two_cta = two_cta_on && !d->a_mn_major && bn == 256 && splits == 1 && d->M > BLOCK_M && max_ctas >= 2;
+    const int b_box_rows = two_cta ? bn / 2 : bn;  // K-major B: rows of the box one CTA loads
+
     GemmKParams kp;
     memset(&kp, 0, sizeof(kp));
     // ---- tensor maps. K-major operand [rows, K]: box {64, rows_tile}.  MN-major operand [K, cols]: box {64, 64}.
@@ -549,7 +758,7 @@ extern "C" int b2d_gemm(const b2d_gemm_desc* d, void* stream_v) {
         if (rc) return rc;
         long long rowsB = d->b_mn_major ? (long long)d->K + (batch - 1) * d->b_boff_row : (long long)d->N + (batch - 1) * d->b_boff_row;
         long long colsB = d->b_mn_major ? (long long)d->N + (batch - 1) * d->b_boff_col : (long long)d->K + (batch - 1) * d->b_boff_col;
-        rc = make_tmap_2d(&kp.tmB, d->B, rowsB, colsB, d->ldb, d->b_mn_major ? 64 : bn, 64);
+        rc = make_tmap_2d(&kp.tmB, d->B, rowsB, colsB, d->ldb, d->b_mn_major ? 64 : b_box_rows, 64);
         if (rc) return rc;
         if (d->K2 > 0) {
             if (d->A2 == nullptr || d->B2 == nullptr) return set_error(B2D_ERR_ARG, "gemm: K2>0 needs A2,B2");
@@ -560,7 +769,7 @@ extern "C" int b2d_gemm(const b2d_gemm_desc* d, void* stream_v) {
             if (d->b_mn_major)
                 rc = make_tmap_2d(&kp.tmB2, d->B2, (long long)d->K2 + (batch - 1) * d->b2_boff_row, d->N, d->ldb2, 64, 64);
             else
-                rc = make_tmap_2d(&kp.tmB2, d->B2, (long long)d->N + (batch - 1) * d->b2_boff_row, d->K2, d->ldb2, bn, 64);
+                rc = make_tmap_2d(&kp.tmB2, d->B2, (long long)d->N + (batch - 1) * d->b2_boff_row, d->K2, d->ldb2, b_box_rows, 64);
             if (rc) return rc;
         }
     }
@@ -601,6 +810,11 @@ extern "C" int b2d_gemm(const b2d_gemm_desc* d, void* stream_v) {
     if (total > 0x7fffffffLL) return set_error(B2D_ERR_SHAPE, "gemm: too many tiles");
     kp.total_work = (int)total;
     int grid = (int)(total < max_ctas ? total : max_ctas);
+    if (two_cta) {
+        const long long pairs = (long long)((kp.m_tiles + 1) / 2) * kp.n_tiles * batch;
+        const int clusters = (int)(pairs < max_ctas / 2 ? pairs : max_ctas / 2);
+        return d->b_mn_major ? launch_gemm2<1>(kp, clusters, stream) : launch_gemm2<0>(kp, clusters, stream);
+    }
 
     switch (bn) {
         case 64: return dispatch_major<64>(kp, d->a_mn_major, d->b_mn_major, grid, stream);

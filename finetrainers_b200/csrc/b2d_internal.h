@@ -38,19 +38,37 @@ int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* d
 // this way.  Off by default (B2D_PDL=1 turns it on): see pdl_enabled() for the measurement.  Works under stream capture.
 bool pdl_enabled();
 
+// cluster_x > 1 launches thread-block clusters of cluster_x consecutive CTAs along x (CTA pairs for cta_group::2 kernels)
 template <typename... P, typename... A>
-inline cudaError_t launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+inline cudaError_t launch_kc(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                             A&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster_x > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)cluster_x;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        ++n;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    return launch_kc(kern, grid, block, smem, st, 1, static_cast<A&&>(args)...);
 }
 
 #define B2D_CHECK_LAUNCH(name)                                                                     \
