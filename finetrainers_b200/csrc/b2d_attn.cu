@@ -5,16 +5,16 @@
 // the sequence) from the SAME shared-memory bytes).  out / dout are token-major [B, S, H*64] so that to_out's GEMM
 // consumes them without a transpose; they are addressed through 4-D tensor maps as well.
 //
-// Forward, one CTA per (128-query tile, b, h), two CTAs co-resident per SM (they interleave MMA and softmax phases):
-//   warp 0: TMA producer (Q once, then K_j/V_j ring)      warp 1: MMA issuer + TMEM owner
-//   warps 2-5: one thread per query row.  S = Q K_j^T lands in TMEM; the thread reads its row with tcgen05.ld (no
-//   shuffles needed for row max / row sum), exponentiates in the log2 domain, writes P (bf16) into 128B-swizzled smem;
-//   O += P V_j accumulates in TMEM; O is only rescaled when the running max moved by more than 2^8 (lazy rescale).
+// Forward (attn_fwd_db_kernel), one CTA per (128-query tile, b, h), two CTAs co-resident per SM:
+//   warp 0: TMA producer (Q once, then 64-row K_j/V_j ring)      warp 1: MMA issuer + TMEM owner
+//   warps 2-5: one thread per query row.  S = Q K_j^T lands in TMEM (double-buffered); the thread reads its row with
+//   tcgen05.ld (no shuffles needed for row max / row sum), exponentiates in the log2 domain, writes P (bf16) into
+//   128B-swizzled smem; O += P V_j accumulates in TMEM; O is only rescaled when a row's maximum grows by more than 2^8.
 //
-// Backward = delta pre-pass + one templated kernel run twice:
+// Backward = delta pre-pass + one templated kernel (attn_bwd_pp_kernel) run twice:
 //   DKV=true : CTA per (key tile j): S^T = K_j Q_i^T, dP^T = V_j dO_i^T, P^T, dS^T -> dV += P^T dO_i, dK += dS^T Q_i
 //   DKV=false: CTA per (query tile i): S = Q_i K_j^T, dP = dO_i V_j^T, dS -> dQ += dS K_j
-// (no atomics, deterministic).
+// (no atomics, deterministic).  Single-key-tile (cross) attention has its own K/V-resident kernels (attn_x*).
 #include <stdlib.h>
 #include "b2d_internal.h"
 #include "b2d_ptx.cuh"
@@ -52,303 +52,6 @@ struct AttnFwdParams {
     float scale_log2;  // scale * log2(e)
 };
 
-constexpr int FWD_KV_STAGES = 2;
-// 112.25 KB: two CTAs (+1 KB reserved each) must fit the SM's 228 KB, so no alignment slack: the dynamic smem window is
-// declared 1024-byte aligned instead.
-constexpr int FWD_SMEM = TILE_BYTES /*Q*/ + FWD_KV_STAGES * 2 * TILE_BYTES /*K,V*/ + 2 * TILE_BYTES /*P*/ + 256;
-
-__global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
-    griddep_launch_dependents();
-    extern __shared__ uint8_t smem_fwd[];  // no static smem in this kernel: the dynamic window starts 1024-aligned
-    uint8_t* smem = smem_fwd;
-    if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzled tiles need a 1024-byte aligned base
-    uint8_t* sQ = smem;
-    uint8_t* sKV = sQ + TILE_BYTES;                        // stage s: K at sKV + s*32K, V at +16K
-    uint8_t* sP = sKV + FWD_KV_STAGES * 2 * TILE_BYTES;    // 2 chunks of [128 x 64] bf16
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TILE_BYTES);
-    uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;   // [2]
-    uint64_t* kv_empty = bars + 3;  // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* p_full = bars + 6;
-    uint64_t* pv_done = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * TILE;
-    const int bh = blockIdx.y;
-    const int b = bh / p.H, h = bh % p.H;
-    const int n_kv = (p.Sk + TILE - 1) / TILE;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.tmQ);
-        tma_prefetch_desc(&p.tmK);
-        tma_prefetch_desc(&p.tmV);
-        mbar_init(q_full, 1);
-        for (int i = 0; i < FWD_KV_STAGES; ++i) {
-            mbar_init(&kv_full[i], 1);
-            mbar_init(&kv_empty[i], 1);
-        }
-        mbar_init(s_full, 1);
-        mbar_init(p_full, 128);
-        mbar_init(pv_done, 1);
-        fence_mbar_init();
-    }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, 256);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    griddep_wait();  // everything above is on-chip setup and overlaps the previous kernel's tail
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t tS = tmem;        // 128 cols
-    const uint32_t tO = tmem + 128;  // 64 cols
-
-    if (warp == 0) {
-        if (elect_one()) {
-            mbar_expect_tx(q_full, TILE_BYTES);
-            tma_load_4d(sQ, &p.tmQ, q_full, 0, h, q0, b);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int j = 0; j < n_kv; ++j) {
-                mbar_wait(&kv_empty[stage], phase ^ 1);
-                mbar_expect_tx(&kv_full[stage], 2 * TILE_BYTES);
-                tma_load_4d(sKV + stage * 2 * TILE_BYTES, &p.tmK, &kv_full[stage], 0, h, j * TILE, b);
-                tma_load_4d(sKV + stage * 2 * TILE_BYTES + TILE_BYTES, &p.tmV, &kv_full[stage], 0, h, j * TILE, b);
-                if (++stage == FWD_KV_STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else if (warp == 1) {
-        if (elect_one()) {
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-            constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
-            mbar_wait(q_full, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint32_t aQ = smem_u32(sQ);
-            const uint32_t aP = smem_u32(sP);
-            for (int j = 0; j < n_kv; ++j) {
-                mbar_wait(&kv_full[stage], phase);
-                tc_fence_after();
-                const uint32_t aK = smem_u32(sKV + stage * 2 * TILE_BYTES);
-                const uint32_t aV = aK + TILE_BYTES;
-                // S = Q K^T   (the previous P V already consumed S's successor state: p_full(j-1) implies S was read)
-                {
-                    const uint32_t lq = sdesc_lo_kmajor(aQ), lk = sdesc_lo_kmajor(aK);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16_lo(tS, lq + k * SDESC_KSTEP_KMAJOR, lk + k * SDESC_KSTEP_KMAJOR, idesc_s, k > 0);
-                }
-                umma_commit(s_full);
-                // O += P V
-                mbar_wait(p_full, j & 1);
-                tc_fence_after();
-                {
-                    const uint32_t lp = sdesc_lo_kmajor(aP), lv = sdesc_lo_mnmajor(aV);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma_f16_lo(tO, lp + (k >> 2) * (TILE_BYTES >> 4) + (k & 3) * SDESC_KSTEP_KMAJOR,
-                                    lv + k * SDESC_KSTEP_MNMAJOR, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-                }
-                umma_commit(&kv_empty[stage]);
-                umma_commit(pv_done);
-                if (++stage == FWD_KV_STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else {
-        const int qd = warp & 3;
-        const int r = qd * 32 + lane;  // row within the tile == TMEM lane
-        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        float m_run = -INFINITY, l_run = 0.f;
-        const float* kb = p.key_bias ? p.key_bias + (long long)b * p.Sk : nullptr;
-        for (int j = 0; j < n_kv; ++j) {
-            mbar_wait(s_full, j & 1);
-            tc_fence_after();
-            const int kv0 = j * TILE;
-            const bool fast = (kb == nullptr) && (kv0 + TILE <= p.Sk);  // full tile, no bias: no per-element masks
-            bool done = false;
-            if (fast && j > 0) {
-                // ---- optimistic single pass: exponentiate against the running max while tracking this tile's max; the
-                // running max is only replaced when a row grows by more than 2^8, which after the first tiles is rare.
-                mbar_wait(pv_done, (j - 1) & 1);  // P buffer free, O quiescent
-                tc_fence_after();
-                float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
-                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-                const float nm = -m_run;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(tS + lane_off + c * 32, v);
-                    tmem_ld_wait();
-                    float pv[32];
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4) {
-                        const float a0 = __uint_as_float(v[e]), a1 = __uint_as_float(v[e + 1]);
-                        const float a2 = __uint_as_float(v[e + 2]), a3 = __uint_as_float(v[e + 3]);
-                        t0 = fmaxf(t0, a0); t1 = fmaxf(t1, a1); t2 = fmaxf(t2, a2); t3 = fmaxf(t3, a3);
-                        pv[e] = fast_exp2(fmaf(a0, p.scale_log2, nm));
-                        pv[e + 1] = fast_exp2(fmaf(a1, p.scale_log2, nm));
-                        pv[e + 2] = fast_exp2(fmaf(a2, p.scale_log2, nm));
-                        pv[e + 3] = fast_exp2(fmaf(a3, p.scale_log2, nm));
-                        l0 += pv[e]; l1 += pv[e + 1]; l2 += pv[e + 2]; l3 += pv[e + 3];
-                    }
-                    uint8_t* chunk = sP + (c >> 1) * TILE_BYTES;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint4 w = make_uint4(pack_bf16x2(pv[u * 8], pv[u * 8 + 1]), pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]),
-                                             pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]), pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]));
-                        *reinterpret_cast<uint4*>(chunk + sw128_off(r, (c & 1) * 4 + u)) = w;
-                    }
-                }
-                const float mxo = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) * p.scale_log2;
-                if (!__any_sync(0xffffffffu, (mxo - m_run) > 8.0f)) {
-                    l_run += (l0 + l1) + (l2 + l3);
-                    done = true;
-                }
-            }
-            if (!done) {
-            // ---- pass 1: row max (log2 domain); 4 independent accumulators keep the FMNMX chain short
-            float mx;
-            if (fast) {
-                float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll 1
-                for (int hf = 0; hf < 2; ++hf) {
-                    uint32_t v0[32], v1[32];
-                    tmem_ld32(tS + lane_off + hf * 64, v0);
-                    tmem_ld32(tS + lane_off + hf * 64 + 32, v1);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4) {
-                        m0 = fmaxf(m0, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
-                        m1 = fmaxf(m1, fmaxf(__uint_as_float(v0[e + 1]), __uint_as_float(v1[e + 1])));
-                        m2 = fmaxf(m2, fmaxf(__uint_as_float(v0[e + 2]), __uint_as_float(v1[e + 2])));
-                        m3 = fmaxf(m3, fmaxf(__uint_as_float(v0[e + 3]), __uint_as_float(v1[e + 3])));
-                    }
-                }
-                mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.scale_log2;  // scale > 0
-            } else {
-                mx = -INFINITY;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(tS + lane_off + c * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int col = kv0 + c * 32 + e;
-                        float x = __uint_as_float(v[e]) * p.scale_log2;
-                        if (kb) x += kb[min(col, p.Sk - 1)] * LOG2E;
-                        x = col < p.Sk ? x : -INFINITY;
-                        mx = fmaxf(mx, x);
-                    }
-                }
-            }
-            // ---- running max with lazy rescale of O
-            float m_use = m_run;
-            if (j == 0) {
-                m_use = mx;
-            } else {
-                const bool need = (mx - m_run) > 8.0f;
-                // P buffer and O are free only once the previous P V has completed
-                mbar_wait(pv_done, (j - 1) & 1);
-                tc_fence_after();
-                if (__any_sync(0xffffffffu, need)) {
-                    if (need) m_use = mx;
-                    const float alpha = fast_exp2(m_run - m_use);
-                    l_run *= alpha;
-#pragma unroll 1
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t v[32];
-                        tmem_ld32(tO + lane_off + c * 32, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-                        tmem_st32(tO + lane_off + c * 32, v);
-                    }
-                    tmem_st_wait();
-                }
-            }
-            m_run = m_use;
-            // ---- pass 2: P = exp2(x - m), row sum (4 accumulators), bf16 -> swizzled smem
-            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld32(tS + lane_off + c * 32, v);
-                tmem_ld_wait();
-                float pv[32];
-                if (fast) {
-                    const float nm = -m_use;
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4) {
-                        pv[e] = fast_exp2(fmaf(__uint_as_float(v[e]), p.scale_log2, nm));
-                        pv[e + 1] = fast_exp2(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, nm));
-                        pv[e + 2] = fast_exp2(fmaf(__uint_as_float(v[e + 2]), p.scale_log2, nm));
-                        pv[e + 3] = fast_exp2(fmaf(__uint_as_float(v[e + 3]), p.scale_log2, nm));
-                        l0 += pv[e]; l1 += pv[e + 1]; l2 += pv[e + 2]; l3 += pv[e + 3];
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int col = kv0 + c * 32 + e;
-                        float x = __uint_as_float(v[e]) * p.scale_log2 - m_use;
-                        if (kb) x += kb[min(col, p.Sk - 1)] * LOG2E;
-                        float pe = col < p.Sk ? fast_exp2(x) : 0.f;
-                        pv[e] = pe;
-                        l0 += pe;
-                    }
-                }
-                uint8_t* chunk = sP + (c >> 1) * TILE_BYTES;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint4 w = make_uint4(pack_bf16x2(pv[u * 8], pv[u * 8 + 1]), pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]),
-                                         pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]), pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]));
-                    *reinterpret_cast<uint4*>(chunk + sw128_off(r, (c & 1) * 4 + u)) = w;
-                }
-            }
-            l_run += (l0 + l1) + (l2 + l3);
-            }  // !done
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(p_full);
-        }
-        // ---- epilogue: O / l -> out (token-major), lse
-        mbar_wait(pv_done, (n_kv - 1) & 1);
-        tc_fence_after();
-        const int qrow = q0 + r;
-        const float inv_l = 1.f / l_run;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tO + lane_off + c * 32, v);
-            tmem_ld_wait();
-            if (qrow < p.Sq) {
-                __nv_bfloat16* o = p.out + ((long long)b * p.Sq + qrow) * (p.H * HD) + h * HD + c * 32;
-#pragma unroll
-                for (int u = 0; u < 2; ++u)  // 2 x 32 B: one full sector per lane and store
-                    st_global_32B(o + u * 16,
-                                  pack_bf16x2(__uint_as_float(v[u * 16]) * inv_l, __uint_as_float(v[u * 16 + 1]) * inv_l),
-                                  pack_bf16x2(__uint_as_float(v[u * 16 + 2]) * inv_l, __uint_as_float(v[u * 16 + 3]) * inv_l),
-                                  pack_bf16x2(__uint_as_float(v[u * 16 + 4]) * inv_l, __uint_as_float(v[u * 16 + 5]) * inv_l),
-                                  pack_bf16x2(__uint_as_float(v[u * 16 + 6]) * inv_l, __uint_as_float(v[u * 16 + 7]) * inv_l),
-                                  pack_bf16x2(__uint_as_float(v[u * 16 + 8]) * inv_l, __uint_as_float(v[u * 16 + 9]) * inv_l),
-                                  pack_bf16x2(__uint_as_float(v[u * 16 + 10]) * inv_l, __uint_as_float(v[u * 16 + 11]) * inv_l),
-                                  pack_bf16x2(__uint_as_float(v[u * 16 + 12]) * inv_l, __uint_as_float(v[u * 16 + 13]) * inv_l),
-                                  pack_bf16x2(__uint_as_float(v[u * 16 + 14]) * inv_l, __uint_as_float(v[u * 16 + 15]) * inv_l));
-            }
-        }
-        if (qrow < p.Sq) p.lse[((long long)b * p.H + h) * p.Sq + qrow] = m_run * LN2 + logf(l_run);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem, 256);
-    }
-}
-
 // ================================================================================================
 // forward, decoupled version: 64-wide key tiles, S DOUBLE-buffered in TMEM (2 x 64 columns + 64 for O = 192 -> 256
 // allocated) and P double-buffered in smem, TWO CTAs per SM.  The MMA warp issues S(j+2) as soon as the softmax warps
@@ -364,7 +67,6 @@ constexpr int FDB_P_BYTES = TILE * FDB_KV * 2;              // 16 KB (one swizzl
 constexpr int FDB_SMEM = TILE_BYTES /*Q*/ + FDB_STAGES * 2 * FDB_KV_BYTES + 2 * FDB_P_BYTES + 256;  // 112.25 KB
 
 __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __grid_constant__ AttnFwdParams p) {
-    griddep_launch_dependents();
     extern __shared__ uint8_t smem_fdb[];  // no static smem: the dynamic window starts 1024-aligned
     uint8_t* smem = smem_fdb;
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -388,8 +90,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmQ);
-        tma_prefetch_desc(&p.tmK);
-        tma_prefetch_desc(&p.tmV);
+        tma_prefetch_desc(&p.tmK64);
+        tma_prefetch_desc(&p.tmV64);
         mbar_init(q_full, 1);
         for (int i = 0; i < FDB_STAGES; ++i) {
             mbar_init(&kv_full[i], 1);
@@ -409,7 +111,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    griddep_wait();  // everything above is on-chip setup and overlaps the previous kernel's tail
     const uint32_t tmem = *tmem_slot;  // S[b] at 64*b, O at 128
     const uint32_t tO = tmem + 128;
 
@@ -632,8 +333,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                                   const float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ nlse2,
                                   int B, int H, int Sq) {
-    griddep_launch_dependents();
-    griddep_wait();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * Sq * H * 8;
     const bool ok = t < total;
@@ -673,281 +372,6 @@ struct AttnBwdParams {
     float scale, scale_log2;
 };
 
-constexpr int BWD_Y_STAGES = 2;
-// TY = rows of the streamed (Y) tile per iteration.  TY = 64 keeps TMEM at 256 columns and smem under 100 KB so that two
-// CTAs share an SM and interleave their MMA and exp/elementwise phases.
-template <int TY>
-struct BwdCfg {
-    static constexpr int Y_BYTES = TY * HD * 2;           // one streamed tile  [TY x 64] bf16
-    static constexpr int PS_BYTES = TILE * TY * 2;        // P^T or dS^T       [128 x TY] bf16 (TY/64 swizzled chunks)
-    static constexpr int SMEM = 2 * TILE_BYTES + BWD_Y_STAGES * 2 * Y_BYTES + 2 * PS_BYTES + BWD_Y_STAGES * 2 * TY * 4 + 1024 + 256;
-    static constexpr int TMEM_COLS = (2 * TY + 128 <= 256) ? 256 : 512;
-};
-
-template <bool DKV, int TY>
-__global__ void __launch_bounds__(ATT_THREADS, (TY == 64 ? 2 : 1)) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
-    griddep_launch_dependents();
-    using Cfg = BwdCfg<TY>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sX1 = smem;
-    uint8_t* sX2 = sX1 + TILE_BYTES;
-    uint8_t* sY = sX2 + TILE_BYTES;                          // stage s: Y1 at +s*2*Y_BYTES, Y2 right after
-    uint8_t* sP = sY + BWD_Y_STAGES * 2 * Cfg::Y_BYTES;      // P^T (DKV only)
-    uint8_t* sDS = sP + Cfg::PS_BYTES;
-    float* sColA = reinterpret_cast<float*>(sDS + Cfg::PS_BYTES);  // [stages][TY]  exponent offsets of the streamed tile
-    float* sColD = sColA + BWD_Y_STAGES * TY;                        // [stages][TY]  delta of the streamed tile
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sColD + BWD_Y_STAGES * TY);
-    uint64_t* x_full = bars;
-    uint64_t* y_full = bars + 1;   // [2]
-    uint64_t* y_empty = bars + 3;  // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* ds_full = bars + 6;
-    uint64_t* mm_done = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x0 = blockIdx.x * TILE;
-    const int bh = blockIdx.y;
-    const int b = bh / p.H, h = bh % p.H;
-    const int rowsX = DKV ? p.Sk : p.Sq;
-    const int rowsY = DKV ? p.Sq : p.Sk;
-    const int n_y_all = (rowsY + TY - 1) / TY;
-    const int y0 = blockIdx.z * p.y_per_split;                     // this CTA streams tiles [y0, y1)
-    const int y1 = min(n_y_all, y0 + p.y_per_split);
-    const int n_y = y1 - y0;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.tmX1);
-        tma_prefetch_desc(&p.tmX2);
-        tma_prefetch_desc(&p.tmY1);
-        tma_prefetch_desc(&p.tmY2);
-        mbar_init(x_full, 1);
-        for (int i = 0; i < BWD_Y_STAGES; ++i) {
-            mbar_init(&y_full[i], 1);
-            mbar_init(&y_empty[i], 1);
-        }
-        mbar_init(s_full, 1);
-        mbar_init(ds_full, 128);
-        mbar_init(mm_done, 1);
-        fence_mbar_init();
-    }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    griddep_wait();  // everything above is on-chip setup and overlaps the previous kernel's tail
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t tS = tmem, tDP = tmem + TY, tO1 = tmem + 2 * TY, tO2 = tmem + 2 * TY + 64;
-
-    if (warp == 0) {
-        if (elect_one()) {
-            mbar_expect_tx(x_full, 2 * TILE_BYTES);
-            tma_load_4d(sX1, &p.tmX1, x_full, 0, h, x0, b);
-            tma_load_4d(sX2, &p.tmX2, x_full, 0, h, x0, b);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int it = 0; it < n_y; ++it) {
-                const int i = y0 + it;
-                mbar_wait(&y_empty[stage], phase ^ 1);
-                // DKV: the per-query exponent offsets (-lse*log2e) and delta of a full tile ride along with the tile
-                const bool colvec = DKV && ((i + 1) * TY <= rowsY) && ((rowsY & 3) == 0);
-                mbar_expect_tx(&y_full[stage], 2 * Cfg::Y_BYTES + (colvec ? 2 * TY * 4 : 0));
-                tma_load_4d(sY + stage * 2 * Cfg::Y_BYTES, &p.tmY1, &y_full[stage], 0, h, i * TY, b);
-                tma_load_4d(sY + stage * 2 * Cfg::Y_BYTES + Cfg::Y_BYTES, &p.tmY2, &y_full[stage], 0, h, i * TY, b);
-                if (colvec) {
-                    const long long off = ((long long)b * p.H + h) * p.Sq + (long long)i * TY;
-                    bulk_load_1d(sColA + stage * TY, p.nlse2 + off, TY * 4, &y_full[stage]);
-                    bulk_load_1d(sColD + stage * TY, p.delta + off, TY * 4, &y_full[stage]);
-                }
-                if (++stage == BWD_Y_STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else if (warp == 1) {
-        if (elect_one()) {
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, TY, 0, 0);
-            constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
-            mbar_wait(x_full, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint32_t aX1 = smem_u32(sX1), aX2 = smem_u32(sX2), aP = smem_u32(sP), aDS = smem_u32(sDS);
-            for (int i = 0; i < n_y; ++i) {  // i = local iteration index
-                mbar_wait(&y_full[stage], phase);
-                tc_fence_after();
-                const uint32_t aY1 = smem_u32(sY + stage * 2 * Cfg::Y_BYTES), aY2 = aY1 + Cfg::Y_BYTES;
-                {
-                    const uint32_t lx1 = sdesc_lo_kmajor(aX1), lx2 = sdesc_lo_kmajor(aX2);
-                    const uint32_t ly1 = sdesc_lo_kmajor(aY1), ly2 = sdesc_lo_kmajor(aY2);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16_lo(tS, lx1 + k * SDESC_KSTEP_KMAJOR, ly1 + k * SDESC_KSTEP_KMAJOR, idesc_s, k > 0);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16_lo(tDP, lx2 + k * SDESC_KSTEP_KMAJOR, ly2 + k * SDESC_KSTEP_KMAJOR, idesc_s, k > 0);
-                }
-                umma_commit(s_full);
-                mbar_wait(ds_full, i & 1);
-                tc_fence_after();
-                if (DKV) {
-                    const uint32_t lp = sdesc_lo_kmajor(aP), ly = sdesc_lo_mnmajor(aY2);
-#pragma unroll
-                    for (int k = 0; k < TY / 16; ++k)  // out1 (dV) += P^T . dO_i   (Y2 as MN-major B)
-                        umma_f16_lo(tO1, lp + (k >> 2) * (TILE_BYTES >> 4) + (k & 3) * SDESC_KSTEP_KMAJOR,
-                                    ly + k * SDESC_KSTEP_MNMAJOR, idesc_o, (i > 0 || k > 0) ? 1u : 0u);
-                }
-                {
-                    const uint32_t ld = sdesc_lo_kmajor(aDS), ly = sdesc_lo_mnmajor(aY1);
-#pragma unroll
-                    for (int k = 0; k < TY / 16; ++k)  // out2 += dS . Y1   (Y1 as MN-major B)
-                        umma_f16_lo(tO2, ld + (k >> 2) * (TILE_BYTES >> 4) + (k & 3) * SDESC_KSTEP_KMAJOR,
-                                    ly + k * SDESC_KSTEP_MNMAJOR, idesc_o, (i > 0 || k > 0) ? 1u : 0u);
-                }
-                umma_commit(&y_empty[stage]);
-                umma_commit(mm_done);
-                if (++stage == BWD_Y_STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else {
-        const int qd = warp & 3;
-        const int r = qd * 32 + lane;
-        const int tid128 = (warp - 2) * 32 + lane;
-        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const int xrow = x0 + r;
-        const bool row_ok = xrow < rowsX;
-        const long long bhoff = (long long)b * p.H + h;
-        // per-row scalars
-        float rowA, rowD = 0.f;
-        if (DKV) {
-            rowA = (p.key_bias && row_ok) ? p.key_bias[(long long)b * p.Sk + xrow] * LOG2E : 0.f;
-        } else {
-            rowA = row_ok ? -p.lse[bhoff * p.Sq + xrow] * LOG2E : 0.f;
-            rowD = row_ok ? p.delta[bhoff * p.Sq + xrow] : 0.f;
-        }
-        if (!row_ok) rowA = -INFINITY;
-        int cstage = 0;
-        uint32_t cphase = 0;
-        for (int it = 0; it < n_y; ++it) {
-            const int i = y0 + it;
-            float* cA = sColA + cstage * TY;
-            float* cD = sColD + cstage * TY;
-            const bool full_tile = (i + 1) * TY <= rowsY;
-            // fast path: DKV -> column vectors arrive by bulk copy with the tile; dQ (self-attention) -> no column terms
-            const bool col_by_copy = DKV && full_tile && ((rowsY & 3) == 0);
-            const bool no_col = !DKV && full_tile && (p.key_bias == nullptr);
-            if (!col_by_copy && !no_col) {
-                // slow path (ragged tail / key bias): the 128 threads fill the column vectors themselves
-                if (tid128 < TY) {
-                    const int ycol = i * TY + tid128;
-                    const bool ok = ycol < rowsY;
-                    if (DKV) {
-                        cA[tid128] = ok ? -p.lse[bhoff * p.Sq + ycol] * LOG2E : -INFINITY;
-                        cD[tid128] = ok ? p.delta[bhoff * p.Sq + ycol] : 0.f;
-                    } else {
-                        cA[tid128] = ok ? (p.key_bias ? p.key_bias[(long long)b * p.Sk + ycol] * LOG2E : 0.f) : -INFINITY;
-                        cD[tid128] = 0.f;
-                    }
-                }
-                named_bar_sync(1, 128);
-            }
-            if (col_by_copy) {
-                mbar_wait(&y_full[cstage], cphase);  // acquire the bulk-copied vectors (the MMA warp waits on it too)
-            }
-            mbar_wait(s_full, it & 1);
-            tc_fence_after();
-            // P / dS smem buffers are free once the previous iteration's MMAs have completed
-            if (it > 0) {
-                mbar_wait(mm_done, (it - 1) & 1);
-                tc_fence_after();
-            }
-#pragma unroll 1
-            for (int c = 0; c < TY / 32; ++c) {
-                uint32_t sv[32], dv[32];
-                tmem_ld32(tS + lane_off + c * 32, sv);
-                tmem_ld32(tDP + lane_off + c * 32, dv);
-                tmem_ld_wait();
-                float pe[32], ds[32];
-                if (no_col) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        float pp = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, rowA));
-                        pe[e] = pp;
-                        ds[e] = pp * (__uint_as_float(dv[e]) - rowD);
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int cc = c * 32 + e;
-                        float pp = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, rowA + cA[cc]));
-                        pe[e] = pp;
-                        ds[e] = pp * (__uint_as_float(dv[e]) - (DKV ? cD[cc] : rowD));
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t off = (uint32_t)((c >> 1) * TILE_BYTES) + sw128_off(r, (c & 1) * 4 + u);
-                    if (DKV) {
-                        uint4 w = make_uint4(pack_bf16x2(pe[u * 8], pe[u * 8 + 1]), pack_bf16x2(pe[u * 8 + 2], pe[u * 8 + 3]),
-                                             pack_bf16x2(pe[u * 8 + 4], pe[u * 8 + 5]), pack_bf16x2(pe[u * 8 + 6], pe[u * 8 + 7]));
-                        *reinterpret_cast<uint4*>(sP + off) = w;
-                    }
-                    uint4 w2 = make_uint4(pack_bf16x2(ds[u * 8], ds[u * 8 + 1]), pack_bf16x2(ds[u * 8 + 2], ds[u * 8 + 3]),
-                                          pack_bf16x2(ds[u * 8 + 4], ds[u * 8 + 5]), pack_bf16x2(ds[u * 8 + 6], ds[u * 8 + 7]));
-                    *reinterpret_cast<uint4*>(sDS + off) = w2;
-                }
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(ds_full);
-            if (++cstage == BWD_Y_STAGES) { cstage = 0; cphase ^= 1; }
-        }
-        // ---- epilogue: accumulators -> [B,H,rowsX,64] bf16 (or fp32 atomics when the streamed range is split over z)
-        if (n_y > 0) {
-            mbar_wait(mm_done, (n_y - 1) & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int which = DKV ? 0 : 1; which < 2; ++which) {
-                const long long ro = (bhoff * rowsX + xrow) * HD;
-                const uint32_t tacc = which == 0 ? tO1 : tO2;
-                const float osc = which == 0 ? 1.f : p.scale;  // dS was kept unscaled: dK, dQ pick up the scale here
-                float* facc = which == 0 ? p.acc1 : p.acc2;
-#pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(tacc + lane_off + c * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * osc);
-                    if (row_ok) {
-                        if (gridDim.z > 1) {
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) atomicAdd(facc + ro + c * 32 + e, __uint_as_float(v[e]));
-                        } else {
-                            __nv_bfloat16* dst = (which == 0 ? p.out1 : p.out2) + ro;
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                uint4 w = make_uint4(pack_bf16x2(__uint_as_float(v[u * 8]), __uint_as_float(v[u * 8 + 1])),
-                                                     pack_bf16x2(__uint_as_float(v[u * 8 + 2]), __uint_as_float(v[u * 8 + 3])),
-                                                     pack_bf16x2(__uint_as_float(v[u * 8 + 4]), __uint_as_float(v[u * 8 + 5])),
-                                                     pack_bf16x2(__uint_as_float(v[u * 8 + 6]), __uint_as_float(v[u * 8 + 7])));
-                                *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = w;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem, Cfg::TMEM_COLS);
-    }
-}
-
 // ================================================================================================
 // backward, pipelined version: ONE CTA per SM.  The S / dP accumulators are TRIPLE-buffered in TMEM (3 x 128 columns +
 // 128 columns of dV/dK or dQ accumulators = all 512), so the MMA warp runs up to three streamed tiles ahead of the two
@@ -968,7 +392,6 @@ constexpr int PP_SMEM = 2 * TILE_BYTES + PP_STAGES * 2 * PP_Y_BYTES + 2 * PP_NBU
 
 template <bool DKV>
 __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid_constant__ AttnBwdParams p) {
-    griddep_launch_dependents();
     constexpr int TY = PP_TY;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1025,7 +448,6 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    griddep_wait();  // everything above is on-chip setup and overlaps the previous kernel's tail
     const uint32_t tmem = *tmem_slot;
     // S[k] at 128*k, dP[k] at 128*k + 64 (k = 0..2), out1 at 384, out2 at 448
     const uint32_t tO1 = tmem + 384, tO2 = tmem + 448;
@@ -1310,7 +732,6 @@ __device__ __forceinline__ void x_load_bias(float* sBias, const float* key_bias,
 }
 
 __global__ void __launch_bounds__(X_THREADS, 1) attn_xfwd_kernel(const __grid_constant__ AttnXParams p) {
-    griddep_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;
@@ -1358,7 +779,6 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xfwd_kernel(const __grid_co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    griddep_wait();  // everything above is on-chip setup and overlaps the previous kernel's tail
     const uint32_t tmem = *tmem_slot;  // S[g] at 128*g, O[g] at 256 + 64*g
 
     if (warp == 0) {
@@ -1517,7 +937,6 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xfwd_kernel(const __grid_co
 }
 
 __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_constant__ AttnXParams p) {
-    griddep_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;
@@ -1570,7 +989,6 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    griddep_wait();  // everything above is on-chip setup and overlaps the previous kernel's tail
     const uint32_t tmem = *tmem_slot;
     // S at 0 (128 key columns), dP at 128, dV at 256, dK at 320, dQ[j] at 384 + 64*j
     const uint32_t tDV = tmem + 256, tDK = tmem + 320;
@@ -1850,8 +1268,6 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_co
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
-    griddep_launch_dependents();
-    griddep_wait();
     long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         float4 v = *reinterpret_cast<const float4*>(src + i);
@@ -1910,12 +1326,7 @@ extern "C" int b2d_attn_fwd(const void* q, const void* k, const void* v, const f
     p.lse = lse;
     p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
     p.scale_log2 = scale * LOG2E;
-    // two kernels: "db" (default for long key sequences: 64-wide key tiles, S/P double-buffered so softmax never waits on
-    // the MMA round trip, 2 CTAs/SM; 120 us at S=2688, H=32, at which point the MUFU ex2 unit is ~85 % busy) and "classic"
-    // (B2D_ATTN_FWD=classic; 128-wide tiles, 2 CTAs/SM interleaving MMA and softmax, 125 us; used when Sk <= 128)
-    static const bool force_classic = []() { const char* e = getenv("B2D_ATTN_FWD"); return e && e[0] == 'c'; }();
-    static const bool cross_general = []() { const char* e = getenv("B2D_ATTN_CROSS"); return e && e[0] == 'g'; }();
-    if (Sk <= TILE && !cross_general) {
+    if (Sk <= TILE) {
         // single key tile (cross attention): K/V-resident kernel walking a range of query tiles per CTA
         AttnXParams x;
         memset(&x, 0, sizeof(x));
@@ -1931,13 +1342,10 @@ extern "C" int b2d_attn_fwd(const void* q, const void* k, const void* v, const f
         B2D_CHECK_LAUNCH("attn_xfwd");
         return 0;
     }
-    if ((rc = set_smem((const void*)attn_fwd_kernel, FWD_SMEM, "attn_fwd"))) return rc;
+    // long key sequences: 64-wide key tiles, S/P double-buffered so softmax never waits on the MMA round trip, 2 CTAs/SM
     if ((rc = set_smem((const void*)attn_fwd_db_kernel, FDB_SMEM, "attn_fwd_db"))) return rc;
     dim3 grid((Sq + TILE - 1) / TILE, B * H);
-    if (!force_classic && Sk > TILE)
-        launch_k(attn_fwd_db_kernel, grid, dim3(ATT_THREADS), FDB_SMEM, reinterpret_cast<cudaStream_t>(stream), p);
-    else
-        launch_k(attn_fwd_kernel, grid, dim3(ATT_THREADS), FWD_SMEM, reinterpret_cast<cudaStream_t>(stream), p);
+    launch_k(attn_fwd_db_kernel, grid, dim3(ATT_THREADS), FDB_SMEM, reinterpret_cast<cudaStream_t>(stream), p);
     B2D_CHECK_LAUNCH("attn_fwd");
     return 0;
 }
@@ -1948,15 +1356,14 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
     B2D_BIND(q);
     if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) return set_error(B2D_ERR_SHAPE, "attn_bwd: bad dims");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    static const bool cross_general = []() { const char* e = getenv("B2D_ATTN_CROSS"); return e && e[0] == 'g'; }();
-    const bool cross = Sk <= TILE && !cross_general;
+    const bool cross = Sk <= TILE;
     if (!cross) {
         long long total = (long long)B * Sq * H * 8;
         launch_k(attn_delta_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const __nv_bfloat16*)out,
                  (const __nv_bfloat16*)dout, lse, delta_ws, delta_ws + (long long)B * H * Sq, B, H, Sq);
         B2D_CHECK_LAUNCH("attn_delta");
     }
-    constexpr int TY = 64;
+    constexpr int TY = PP_TY;
     CUtensorMap mQ, mK, mV, mdO, mQy, mKy, mVy, mdOy;  // X role: 128-row boxes; Y role: TY-row boxes
     int rc;
     if ((rc = make_head_map(&mQ, q, B, H, Sq, (long long)Sq * 64, 64, (long long)H * Sq * 64))) return rc;
@@ -1997,16 +1404,14 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
     p.key_bias = key_bias; p.lse = lse; p.delta = delta_ws; p.nlse2 = delta_ws + (long long)B * H * Sq;
     p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
     p.scale = scale; p.scale_log2 = scale * LOG2E;
-    // dK, dV.  With few key tiles (cross attention: Sk = 128 -> B*H CTAs) the query range is split over gridDim.z and
-    // the partial dK/dV are accumulated with fp32 atomics in the tail of delta_ws, then rounded to bf16.
+    // dK, dV.  With few key tiles (128 < Sk <= 512 and few heads) the query range is split over gridDim.z and the
+    // partial dK/dV are accumulated with fp32 atomics in the tail of delta_ws, then rounded to bf16.
     p.tmX1 = mK; p.tmX2 = mV; p.tmY1 = mQy; p.tmY2 = mdOy;
     p.out1 = (__nv_bfloat16*)dv; p.out2 = (__nv_bfloat16*)dk;
-    static const bool use_pp = []() { const char* e = getenv("B2D_ATTN_BWD"); return !(e && e[0] == 'c'); }();
     const int n_yq = (Sq + TY - 1) / TY;
     const int kv_ctas = ((Sk + TILE - 1) / TILE) * B * H;
     int splits = 1;
     if (kv_ctas < 96 && Sk <= 512 && n_yq >= 8) splits = min(min(8, n_yq / 4), (2 * 148 + kv_ctas - 1) / kv_ctas);
-    if ((rc = set_smem((const void*)attn_bwd_kernel<true, TY>, BwdCfg<TY>::SMEM, "attn_bwd_dkv"))) return rc;
     if ((rc = set_smem((const void*)attn_bwd_pp_kernel<true>, PP_SMEM, "attn_bwd_pp_dkv"))) return rc;
     if ((rc = set_smem((const void*)attn_bwd_pp_kernel<false>, PP_SMEM, "attn_bwd_pp_dq"))) return rc;
     p.y_per_split = (n_yq + splits - 1) / splits;
@@ -2016,19 +1421,13 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
         p.acc2 = p.acc1 + n_kv;
         cudaError_t e = cudaMemsetAsync(p.acc1, 0, 2 * n_kv * sizeof(float), st);
         if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "attn_bwd memset: %s", cudaGetErrorString(e));
-        if (use_pp)
-            launch_k(attn_bwd_pp_kernel<true>, dim3((Sk + TILE - 1) / TILE, B * H, splits), dim3(PP_THREADS), PP_SMEM, st, p);
-        else
-            launch_k(attn_bwd_kernel<true, TY>, dim3((Sk + TILE - 1) / TILE, B * H, splits), dim3(ATT_THREADS), BwdCfg<TY>::SMEM, st, p);
+        launch_k(attn_bwd_pp_kernel<true>, dim3((Sk + TILE - 1) / TILE, B * H, splits), dim3(PP_THREADS), PP_SMEM, st, p);
         B2D_CHECK_LAUNCH("attn_bwd_dkv(split)");
         launch_k(f32_to_bf16_kernel, dim3((unsigned)((n_kv / 4 + 255) / 256)), dim3(256), 0, st, p.acc1, (__nv_bfloat16*)dv, n_kv);
         launch_k(f32_to_bf16_kernel, dim3((unsigned)((n_kv / 4 + 255) / 256)), dim3(256), 0, st, p.acc2, (__nv_bfloat16*)dk, n_kv);
         B2D_CHECK_LAUNCH("attn_bwd_dkv(convert)");
     } else {
-        if (use_pp)
-            launch_k(attn_bwd_pp_kernel<true>, dim3((Sk + TILE - 1) / TILE, B * H), dim3(PP_THREADS), PP_SMEM, st, p);
-        else
-            launch_k(attn_bwd_kernel<true, TY>, dim3((Sk + TILE - 1) / TILE, B * H), dim3(ATT_THREADS), BwdCfg<TY>::SMEM, st, p);
+        launch_k(attn_bwd_pp_kernel<true>, dim3((Sk + TILE - 1) / TILE, B * H), dim3(PP_THREADS), PP_SMEM, st, p);
         B2D_CHECK_LAUNCH("attn_bwd_dkv");
     }
     p.acc1 = p.acc2 = nullptr;
@@ -2036,11 +1435,7 @@ extern "C" int b2d_attn_bwd(const void* q, const void* k, const void* v, const f
     p.tmX1 = mQ; p.tmX2 = mdO; p.tmY1 = mKy; p.tmY2 = mVy;
     p.out1 = nullptr; p.out2 = (__nv_bfloat16*)dq;
     p.y_per_split = (Sk + TY - 1) / TY;
-    if ((rc = set_smem((const void*)attn_bwd_kernel<false, TY>, BwdCfg<TY>::SMEM, "attn_bwd_dq"))) return rc;
-    if (use_pp)
-        launch_k(attn_bwd_pp_kernel<false>, dim3((Sq + TILE - 1) / TILE, B * H), dim3(PP_THREADS), PP_SMEM, st, p);
-    else
-        launch_k(attn_bwd_kernel<false, TY>, dim3((Sq + TILE - 1) / TILE, B * H), dim3(ATT_THREADS), BwdCfg<TY>::SMEM, st, p);
+    launch_k(attn_bwd_pp_kernel<false>, dim3((Sq + TILE - 1) / TILE, B * H), dim3(PP_THREADS), PP_SMEM, st, p);
     B2D_CHECK_LAUNCH("attn_bwd_dq");
     return 0;
 }

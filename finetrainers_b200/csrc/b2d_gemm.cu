@@ -250,7 +250,6 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmKParams& p, int mt,
 
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmKParams p) {
-    griddep_launch_dependents();
     using Cfg = GemmCfg<BN, B_MN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -287,7 +286,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    griddep_wait();  // everything above is on-chip setup and overlaps the previous kernel's tail
     const uint32_t tmem_base = *tmem_slot;
 
     const int kb_total = p.kb_main + p.kb_ext;  // per work item when splits == 1
@@ -784,7 +782,7 @@ extern "C" int b2d_gemm(const b2d_gemm_desc* d, void* stream_v) {
     if (d->a2_boff_row < 0 || d->b2_boff_row < 0 || d->bias_boff < 0 || (d->bias_boff % 8) != 0)
         return set_error(B2D_ERR_ARG, "gemm: extension/bias batch offsets must be >= 0 (bias_boff a multiple of 8)");
     kp.epi = d->epi;
-    kp.alpha = d->alpha == 0.f ? 1.f : d->alpha;
+    kp.alpha = d->alpha;
     kp.out = d->out; kp.ldc = d->ldc;
     kp.out2 = d->out2; kp.ldc2 = d->ldc2;
     kp.bias = (const __nv_bfloat16*)d->bias;

@@ -31,13 +31,6 @@ int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long c
 int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                  const uint32_t* box, int elem_bytes, int swizzle128);
 
-// Programmatic dependent launch: kernels started through launch_k carry cudaLaunchAttributeProgrammaticStreamSerialization,
-// so the grid is pre-launched while its stream predecessor drains (its on-chip prologue - barrier init, TMEM allocation,
-// tensor-map prefetch - overlaps the predecessor's tail) and blocks in griddepcontrol.wait until the predecessor has
-// completed and flushed.  ONLY kernels that execute griddep_wait() before their first global access may be launched
-// this way.  Off by default (B2D_PDL=1 turns it on): see pdl_enabled() for the measurement.  Works under stream capture.
-bool pdl_enabled();
-
 // cluster_x > 1 launches thread-block clusters of cluster_x consecutive CTAs along x (CTA pairs for cta_group::2 kernels)
 template <typename... P, typename... A>
 inline cudaError_t launch_kc(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
@@ -47,13 +40,8 @@ inline cudaError_t launch_kc(void (*kern)(P...), dim3 grid, dim3 block, size_t s
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[2];
+    cudaLaunchAttribute at[1];
     int n = 0;
-    if (pdl_enabled()) {
-        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[n].val.programmaticStreamSerializationAllowed = 1;
-        ++n;
-    }
     if (cluster_x > 1) {
         at[n].id = cudaLaunchAttributeClusterDimension;
         at[n].val.clusterDim.x = (unsigned)cluster_x;

@@ -186,15 +186,6 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
 }
 
-// programmatic dependent launch (see launch_k in b2d_internal.h): let the next grid in the stream be pre-launched /
-// block until the previous grid has completed and its memory is visible.  Both are no-ops for a plain launch.
-__device__ __forceinline__ void griddep_launch_dependents() {
-#ifdef B2D_PDL_EARLY_TRIGGER
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 // 256-bit store (sm_100 STG.256): one full 32-byte sector per lane.  One thread owns a row here, so a warp-wide 16-byte
 // store leaves 32 half-written sectors behind; the 32-byte form halves both the store instructions and the L2 write requests.
 __device__ __forceinline__ void st_global_32B(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,

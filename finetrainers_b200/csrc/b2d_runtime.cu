@@ -20,31 +20,22 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 // The library links its own (static) CUDA runtime, whose per-thread "current device" is independent of the caller's
-// (PyTorch's) runtime.  Autograd runs backward on a fresh host thread, so every entry point binds the calling thread to
-// the device that owns the buffers it was handed (once per thread).
+// (PyTorch's) runtime.  Autograd runs backward on a fresh host thread, and one process may drive several GPUs, so every
+// entry point looks up the device that owns the buffer it was handed and makes it current for the calling thread
+// whenever it differs from the one this thread was last bound to.
 int bind_thread(const void* device_ptr) {
     static thread_local int bound = -1;
-    if (bound >= 0) return B2D_OK;
     cudaPointerAttributes at;
     cudaError_t e = cudaPointerGetAttributes(&at, device_ptr);
     if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "cudaPointerGetAttributes: %s", cudaGetErrorString(e));
     if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)
         return set_error(B2D_ERR_ARG, "libb2d needs device pointers (got host/unregistered memory): no CPU fallback");
+    if (at.device == bound) return B2D_OK;
     e = cudaSetDevice(at.device);
     if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "cudaSetDevice(%d): %s", at.device, cudaGetErrorString(e));
     cudaFree(0);  // make the primary context current for driver-API calls (cuTensorMapEncodeTiled)
     bound = at.device;
     return B2D_OK;
-}
-
-bool pdl_enabled() {
-    static const bool on = []() {
-        // opt-in: measured on B200 inside the step's CUDA graph, programmatic edges were 1.7-2.5 % SLOWER than plain
-        // edges (39.1-39.4 vs 38.4 ms/step), with or without an early griddepcontrol.launch_dependents
-        const char* e = getenv("B2D_PDL");
-        return e && e[0] == '1';
-    }();
-    return on;
 }
 
 int device_sm_count() {

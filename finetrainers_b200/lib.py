@@ -49,9 +49,16 @@ class GemmDesc(C.Structure):
 
 
 def build(verbose: bool = False) -> str:
-    """Compile libb2d.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    """Compile libb2d.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).  Serialised across processes
+    with a file lock: N torchrun ranks on a source-only checkout must not link the same output concurrently."""
+    import fcntl
     cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j", str(min(8, os.cpu_count() or 1))]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    with open(os.path.join(_HERE, "csrc", ".build.lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
     if r.returncode != 0:
         raise B2DError("building libb2d.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
     if verbose:

@@ -162,11 +162,16 @@ class _StepFn(torch.autograd.Function):
     def forward(ctx, anchor, model, hidden_states, encoder_hidden_states, tvals, key_bias, num_frames, height, width,
                 rope_scale):
         ctx.model = model
-        return model._forward_impl(hidden_states, encoder_hidden_states, tvals, key_bias, num_frames, height, width,
-                                   rope_scale)
+        out = model._forward_impl(hidden_states, encoder_hidden_states, tvals, key_bias, num_frames, height, width,
+                                  rope_scale)
+        ctx.gen = model._fwd_gen
+        return out
 
     @staticmethod
     def backward(ctx, dpred):
+        if ctx.gen != ctx.model._fwd_gen:
+            raise RuntimeError("B200LTXTransformer keeps ONE set of saved activations: another forward ran between this "
+                               "forward and its backward (validation pass, second micro-batch, ...); call backward first")
         ctx.model._backward_impl(dpred)
         return (None,) * 10
 
@@ -199,15 +204,65 @@ class B200LTXTransformer(nn.Module):
         self._rope: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._anchor = torch.zeros((), dtype=torch.float32, device=device, requires_grad=True)
         self._saved_key = None
+        self._fwd_gen = 0
         self.skip_block0_dx = True
 
     # ------------------------------------------------------------------------------------------------
     # adapters / packing
     # ------------------------------------------------------------------------------------------------
-    def add_adapter(self, rank: int = 64, lora_alpha: Optional[float] = None, target_modules=LORA_TARGETS):
-        """``transformer.add_adapter(LoraConfig(r, lora_alpha, target_modules))`` (trainer.py:120-128)."""
-        if set(target_modules) != set(LORA_TARGETS):
-            raise NotImplementedError("b200 engine fuses LoRA on to_q|to_k|to_v|to_out.0 of attn1+attn2")
+    def _resolve_lora_targets(self, target_modules) -> List[str]:
+        """peft's matching rule (``peft.tuners.tuners_utils.check_target_module_exists``): a ``str`` is a regex that must
+        FULL-match the module name, a list matches by exact name or ``.``-suffix.  Returns the matched linear FQNs."""
+        import re
+        names = [n for n, m in self.named_modules() if isinstance(m, ParamLinear) and ".lora_" not in n]
+        names = [n[:-len(".base_layer")] if n.endswith(".base_layer") else n for n in names]
+        if isinstance(target_modules, str):
+            return [n for n in names if re.fullmatch(target_modules, n)]
+        tm = list(target_modules)
+        return [n for n in names if any(n == t or n.endswith("." + t) for t in tm)]
+
+    def add_adapter(self, adapter_config=None, lora_alpha: Optional[float] = None, target_modules=None,
+                    adapter_name: str = "default"):
+        """``transformer.add_adapter(LoraConfig(r=, lora_alpha=, init_lora_weights=True, target_modules=))`` exactly as
+        ``SFTTrainer._prepare_trainable_parameters`` calls it (trainer.py:120-128): the first positional argument is a
+        peft-style config object (anything with ``.r``, ``.lora_alpha``, ``.target_modules`` and optionally
+        ``.init_lora_weights``).  ``add_adapter(64, 64)`` (rank, alpha) is kept as a shorthand.  ``target_modules`` follows
+        peft's matching rule and must select exactly the attention projections the engine fuses
+        (to_q|to_k|to_v|to_out.0 of attn1 + attn2 in every block: the reference default regex, config.py:26)."""
+        init = True
+        if adapter_config is None:
+            rank = 64
+        elif hasattr(adapter_config, "r"):
+            rank = int(adapter_config.r)
+            if lora_alpha is None:
+                lora_alpha = getattr(adapter_config, "lora_alpha", None)
+            if target_modules is None:
+                target_modules = getattr(adapter_config, "target_modules", None)
+            init = getattr(adapter_config, "init_lora_weights", True)
+            if getattr(adapter_config, "lora_dropout", 0.0):
+                raise NotImplementedError("lora_dropout > 0 is not supported (the reference never sets it)")
+        else:
+            rank = int(adapter_config)
+        if adapter_name != "default":
+            raise NotImplementedError("only the 'default' adapter name is supported")
+        if self.lora_rank:
+            raise ValueError("an adapter is already attached")
+        if rank <= 0:
+            raise ValueError("LoRA rank must be positive")
+        if init not in (True, "gaussian"):
+            raise NotImplementedError(f"init_lora_weights={init!r}: only True (kaiming-uniform A, zero B) and 'gaussian'")
+        if target_modules is None:
+            target_modules = LORA_TARGETS
+        if isinstance(target_modules, (set, frozenset)):
+            target_modules = sorted(target_modules)
+        want = sorted(f"transformer_blocks.{i}.{a}.{t}" for i in range(len(self.transformer_blocks))
+                      for a in ("attn1", "attn2") for t in LORA_TARGETS)
+        got = sorted(self._resolve_lora_targets(target_modules))
+        if got != want:
+            extra = [n for n in got if n not in want][:4]
+            missing = [n for n in want if n not in got][:4]
+            raise NotImplementedError("b200 engine fuses LoRA on to_q|to_k|to_v|to_out.0 of attn1+attn2 of every block; "
+                                      f"target_modules selects a different set (extra: {extra}, missing: {missing})")
         alpha = float(lora_alpha if lora_alpha is not None else rank)
         for p in self.parameters():
             p.requires_grad_(False)
@@ -217,9 +272,44 @@ class B200LTXTransformer(nn.Module):
                 attn.to_k = LoraLinear(attn.to_k, rank, alpha)
                 attn.to_v = LoraLinear(attn.to_v, rank, alpha)
                 attn.to_out[0] = LoraLinear(attn.to_out[0], rank, alpha)
+        if init == "gaussian":  # peft: A ~ N(0, 1/r), B = 0
+            with torch.no_grad():
+                for n, p in self.named_parameters():
+                    if "lora_A" in n:
+                        p.normal_(0.0, 1.0 / rank)
         self.lora_rank = rank
         self.lora_scaling = alpha / rank
+        self.peft_config = {adapter_name: adapter_config if hasattr(adapter_config, "r") else None}
+        self._lora_init = init
+        self._lora_targets = target_modules
         self._prepared = False
+
+    def _apply(self, fn, recurse=True):
+        """``.to()`` / ``.cuda()`` / ``.float()`` replace parameter storage when the dtype or device changes, which would
+        silently detach the parameters from the packed buffers the kernels read.  Re-pack in that case (values are taken
+        from the moved parameters; the fp32 LoRA masters stay fp32, the reference's own policy under DDP,
+        trainer.py:130-136)."""
+        was = getattr(self, "_prepared", False)
+        probe = self.proj_in.weight
+        probes = [self.proj_in.weight]
+        if len(self.transformer_blocks):
+            blk = self.transformer_blocks[0]
+            probes.append(blk.ff.net[2].weight)
+            if self.lora_rank:
+                probes.append(blk.attn1.to_q.lora_A["default"].weight)
+        before = [(q.data_ptr(), q.dtype) for q in probes]
+        stash = self.lora_flat.clone() if (was and self.lora_rank) else None  # a dtype cast must not round the fp32 masters
+        out = super()._apply(fn, recurse)
+        if self._anchor.device != probe.device:
+            self._anchor = torch.zeros((), dtype=torch.float32, device=probe.device, requires_grad=True)
+        if was and before != [(q.data_ptr(), q.dtype) for q in probes]:
+            self._prepared = False
+            self._ws.clear()
+            self._rope.clear()
+            self.prepare()
+            if stash is not None:
+                self.lora_flat.copy_(stash.to(self.lora_flat.device))
+        return out
 
     def lora_parameters(self) -> List[nn.Parameter]:
         return [p for n, p in self.named_parameters() if "lora_" in n]
@@ -239,8 +329,10 @@ class B200LTXTransformer(nn.Module):
         from safetensors.torch import save_file
         os.makedirs(directory, exist_ok=True)
         sd = {"transformer." + k: v for k, v in self.lora_state_dict().items()}
+        tm = getattr(self, "_lora_targets", LORA_TARGETS)
         meta = {"format": "pt", "lora_config": json.dumps({"r": self.lora_rank, "lora_alpha": self.lora_rank * self.lora_scaling,
-                                                           "target_modules": list(LORA_TARGETS)})}
+                                                           "target_modules": tm if isinstance(tm, str) else list(tm),
+                                                           "init_lora_weights": getattr(self, "_lora_init", True)})}
         meta.update(metadata or {})
         path = os.path.join(directory, "pytorch_lora_weights.safetensors")
         save_file(sd, path, metadata=meta)
@@ -462,6 +554,7 @@ class B200LTXTransformer(nn.Module):
         R, RL = B * S, B * L
         ws = self._workspace(B, S, L)
         self._saved_key = (B, S, L, Fr, Hh, Ww, rope_scale)
+        self._fwd_gen += 1
         self._key_bias = key_bias
         cos, sin = self._rope_tables(Fr, Hh, Ww, rope_scale)
         x_in = hidden_states.reshape(R, Cin).to(torch.bfloat16).contiguous()

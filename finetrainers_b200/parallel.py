@@ -21,7 +21,8 @@ import torch.distributed as dist
 
 def _avg_all_reduce(t: torch.Tensor, group=None) -> torch.Tensor:
     """AVG all-reduce that also works on the gloo backend (CPU tests): SUM then divide."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    group = _group_of(group)
+    if group is _UNIT_GROUP or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return t
     if dist.get_backend(group) == "nccl":
         dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
@@ -41,25 +42,32 @@ def dist_max(x: torch.Tensor, group=None) -> float:
     """parallel/utils.py:13-15."""
     assert x.numel() == 1
     y = x.clone()
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    group = _group_of(group)
+    if group is not _UNIT_GROUP and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(y, op=dist.ReduceOp.MAX, group=group)
     return y.item()
 
 
 def fused_step_metrics(grad_norm: torch.Tensor, loss: torch.Tensor, group=None) -> Dict[str, float]:
-    """grad_norm AVG, loss AVG, loss MAX (trainer.py:507-520) with two tiny collectives and ONE host sync."""
-    avg = torch.stack([grad_norm.reshape(()), loss.reshape(())]).float()
-    mx = loss.reshape(1).float().clone()
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        _avg_all_reduce(avg, group)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-    g, l = avg.tolist()
-    return {"train/grad_norm": g, "train/global_avg_loss": l, "train/global_max_loss": mx.item()}
+    """grad_norm AVG, loss AVG, loss MAX over the data-parallel group (trainer.py:507-520: three collectives and up to
+    five ``.item()`` syncs there) as ONE all-gather of two floats per rank and ONE host sync."""
+    mine = torch.stack([grad_norm.reshape(()).float(), loss.reshape(()).float()])
+    group = _group_of(group)
+    if group is not _UNIT_GROUP and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        allv = torch.empty(dist.get_world_size(group) * 2, dtype=torch.float32, device=mine.device)
+        dist.all_gather_into_tensor(allv, mine, group=group)
+        rows = allv.view(-1, 2).tolist()
+    else:
+        rows = [mine.tolist()]
+    n = len(rows)
+    return {"train/grad_norm": sum(r[0] for r in rows) / n, "train/global_avg_loss": sum(r[1] for r in rows) / n,
+            "train/global_max_loss": max(r[1] for r in rows)}
 
 
 def allreduce_flat_grads(flat_grad: torch.Tensor, group=None, chunk_bytes: int = 0) -> torch.Tensor:
     """Average the flat gradient buffer in place.  ``chunk_bytes`` > 0 issues several collectives (bucket_cap_mb-style)."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    group = _group_of(group)
+    if group is _UNIT_GROUP or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return flat_grad
     if chunk_bytes <= 0:
         return _avg_all_reduce(flat_grad, group)
@@ -69,14 +77,71 @@ def allreduce_flat_grads(flat_grad: torch.Tensor, group=None, chunk_bytes: int =
     return flat_grad
 
 
+class B200Mesh:
+    """Stand-in for the ``torch.distributed.DeviceMesh`` the reference builds (ptd.py:182-219) restricted to what this
+    backend supports: ONE data-parallel dimension (replicated = DDP, or sharded = FSDP-2); pp / cp / tp have size 1.
+    ``mesh[name]`` (a name or a tuple of names, as trainer.py:166-183 builds them) returns a sub-mesh with
+    ``get_group()`` / ``size()`` / ``get_local_rank()`` / ``ndim``; the data-parallel names all map to the world group."""
+    _DP_NAMES = ("dp", "dp_cp", "dp_replicate", "dp_shard", "dp_shard_cp")
+    _UNIT_NAMES = ("pp", "cp", "tp")
+
+    def __init__(self, world: int, rank: int, sharded: bool, names=None, group="world"):
+        self._world, self._rank, self._sharded = world, rank, sharded
+        self.mesh_dim_names = tuple(names) if names is not None else (("dp_shard_cp",) if sharded else ("dp_replicate",))
+        self._group = group
+
+    @property
+    def ndim(self) -> int:
+        return 1
+
+    def size(self, mesh_dim: Optional[int] = None) -> int:
+        return self._world if self._group == "world" else 1
+
+    def get_local_rank(self, mesh_dim=None) -> int:
+        return self._rank if self._group == "world" else 0
+
+    def get_group(self, mesh_dim=None):
+        """None = the default (world) process group for the data-parallel views; unit meshes have no peers."""
+        if self._group != "world":
+            return _UNIT_GROUP
+        return dist.group.WORLD if dist.is_initialized() else None
+
+    def __getitem__(self, name):
+        names = (name,) if isinstance(name, str) else tuple(name)
+        for n in names:
+            if n not in self._DP_NAMES + self._UNIT_NAMES:
+                raise KeyError(f"mesh dimension {n!r} does not exist (have {self._DP_NAMES + self._UNIT_NAMES})")
+        unit = all(n in self._UNIT_NAMES for n in names)
+        return B200Mesh(self._world, self._rank, self._sharded, names, "unit" if unit else "world")
+
+    def __repr__(self):
+        return f"B200Mesh({self.mesh_dim_names}, size={self.size()})"
+
+
+_UNIT_GROUP = object()  # marker: a mesh dimension of size 1 (no collective is ever issued on it)
+
+
+def _group_of(mesh_or_group):
+    """Accept what the reference passes (a mesh, ``parallel/utils.py:6-19``) or a raw process group / None."""
+    if isinstance(mesh_or_group, B200Mesh):
+        return mesh_or_group.get_group()
+    return mesh_or_group
+
+
 class B200ParallelBackend:
     """Same surface as ``PytorchDTensorParallelBackend`` for the calls the SFT loop makes (ptd.py:41-279)."""
 
-    def __init__(self, world_size: Optional[int] = None, dp_degree: Optional[int] = None, backend: str = "nccl",
-                 timeout: int = 180, device_type: str = "cuda", **unsupported_degrees):
-        for k, v in unsupported_degrees.items():
-            if k in ("pp_degree", "dp_shards", "cp_degree", "tp_degree") and v not in (None, 1):
-                raise NotImplementedError(f"{k}={v}: only data-parallel replication (DDP) is built (SURVEY §2.2)")
+    def __init__(self, world_size: Optional[int] = None, dp_degree: Optional[int] = None, dp_shards: int = 1,
+                 backend: str = "nccl", timeout: int = 180, device_type: str = "cuda", **other_degrees):
+        """Same keyword names as ``PytorchDTensorParallelBackend.__init__`` (ptd.py:41-57).  Supported layouts: pure
+        replication (``dp_degree == world``, DDP) or pure sharding (``dp_shards == world``, FSDP-2); pp / cp / tp must be 1
+        and HSDP (both > 1) is not built (out of scope for the LTX path)."""
+        for k, v in other_degrees.items():
+            if k in ("pp_degree", "cp_degree", "tp_degree"):
+                if v not in (None, 1):
+                    raise NotImplementedError(f"{k}={v}: only data parallelism is built (SURVEY section 2.2)")
+            elif k not in ("logging_dir", "output_dir", "gradient_accumulation_steps"):
+                raise TypeError(f"unexpected argument {k!r}")
         self._device_type = device_type
         if not dist.is_initialized() and int(os.environ.get("WORLD_SIZE", "1")) > 1:
             dist.init_process_group(backend=backend, timeout=datetime.timedelta(seconds=timeout))
@@ -85,12 +150,21 @@ class B200ParallelBackend:
         self._local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         if world_size is not None and world_size != self._world:
             raise ValueError(f"world_size {world_size} != launched world {self._world}")
-        self._dp_degree = dp_degree or self._world
-        if self._dp_degree != self._world:
-            raise ValueError("the b200 backend is pure data parallel: dp_degree must equal world_size")
+        dp_shards = 1 if dp_shards in (None, -1) else int(dp_shards)
+        if dp_shards > 1:
+            if dp_degree not in (None, 1):
+                raise NotImplementedError("HSDP (dp_degree > 1 together with dp_shards > 1) is not built")
+            if dp_shards != self._world:
+                raise ValueError(f"dp_shards {dp_shards} must equal world_size {self._world}")
+            self._dp_degree, self._dp_shards = 1, dp_shards
+        else:
+            self._dp_degree, self._dp_shards = dp_degree or self._world, 1
+            if self._dp_degree != self._world:
+                raise ValueError("the b200 backend is pure data parallel: dp_degree (or dp_shards) must equal world_size")
         if device_type == "cuda":
             torch.cuda.set_device(self._local_rank)
         self.tracker = None
+        self._mesh = None
 
     # --- model / optimizer preparation -------------------------------------------------------------------------
     def apply_ddp(self, model: torch.nn.Module, device_mesh=None) -> torch.nn.Module:
@@ -126,7 +200,11 @@ class B200ParallelBackend:
         return torch.utils.data.DataLoader(dataset, batch_size=batch_size, num_workers=num_workers, pin_memory=pin_memory)
 
     def get_mesh(self, name: Optional[str] = None):
-        return {"dp": None, "dp_cp": None, "dp_replicate": None}.get(name) if name else {"dp": None, "dp_cp": None}
+        """``get_mesh()`` / ``get_mesh()[name]`` as the SFT loop indexes it (trainer.py:144,150,183,186,492,512,595): a
+        1-D data-parallel mesh whose every named view the loop asks for resolves to a process group."""
+        if self._mesh is None:
+            self._mesh = B200Mesh(self._world, self._rank, self._dp_shards > 1)
+        return self._mesh[name] if name is not None else self._mesh
 
     def get_checkpointer(self, *args, **kwargs):
         raise NotImplementedError("checkpointing stays with the caller (parameter FQNs are diffusers/peft compatible)")
@@ -186,11 +264,11 @@ class B200ParallelBackend:
 
     @property
     def data_replication_enabled(self):
-        return self._world > 1
+        return self._dp_degree > 1
 
     @property
     def data_sharding_enabled(self):
-        return False
+        return self._dp_shards > 1
 
     @property
     def context_parallel_enabled(self):

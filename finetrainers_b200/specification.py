@@ -33,6 +33,15 @@ class LTXVideoModelSpecification:
         transformer = B200LTXTransformer(self.transformer_config, self.transformer_dtype, device)
         return {"transformer": transformer, "scheduler": FlowMatchSchedulerTable()}
 
+    # -- modeling_utils.py:156-181
+    def collate_conditions(self, data):
+        from .data import collate
+        return collate(data)
+
+    def collate_latents(self, data):
+        from .data import collate
+        return collate(data)
+
     def forward(self, transformer: B200LTXTransformer, condition_model_conditions: Dict[str, torch.Tensor],
                 latent_model_conditions: Dict[str, torch.Tensor], sigmas: torch.Tensor,
                 generator: Optional[torch.Generator] = None, compute_posterior: bool = True,

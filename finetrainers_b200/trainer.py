@@ -20,6 +20,7 @@ from . import ops
 from .model import B200LTXTransformer
 from .specification import LTXVideoModelSpecification, FlowMatchSchedulerTable
 from .lr_schedule import lr_factor_fn
+from .parallel import allreduce_flat_grads, fused_step_metrics
 
 
 def compute_density_for_timestep_sampling(weighting_scheme: str, batch_size: int, logit_mean: float = 0.0,
@@ -184,6 +185,9 @@ class SFTTrainStep:
         if "latents_mean" in latent_model_conditions:
             st["mean"].copy_(latent_model_conditions["latents_mean"].reshape(B, C), non_blocking=True)
             st["std"].copy_(latent_model_conditions["latents_std"].reshape(B, C), non_blocking=True)
+        else:  # already-normalised latents: do not keep a previous batch's statistics in the static buffers
+            st["mean"].zero_()
+            st["std"].fill_(1.0)
         st["ehs"].copy_(ehs, non_blocking=True)
         if mask is not None:
             st["mask"].copy_(mask, non_blocking=True)
@@ -223,7 +227,7 @@ class SFTTrainStep:
         g = tr.lora_grad_flat
         if self.world > 1:
             # DDP: average the flat fp32 gradient buffer in place over NVLink (ptd.py:462-463 replicate(bucket_cap_mb=100))
-            torch.distributed.all_reduce(g, op=torch.distributed.ReduceOp.AVG, group=self.pg)
+            allreduce_flat_grads(g, self.pg)
         self.sumsq.zero_()
         ops.sumsq(g, g.numel(), self.sumsq, self.partial)
         self.opt_step += 1
@@ -237,15 +241,7 @@ class SFTTrainStep:
         self.micro = 0
         if not sync_metrics:
             return None
-        m = self.metrics.clone()
-        if self.world > 1:
-            avg = m[:2].clone()
-            torch.distributed.all_reduce(avg, op=torch.distributed.ReduceOp.AVG, group=self.pg)
-            mx = m[2:].clone()
-            torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX, group=self.pg)
-            m = torch.cat([avg, mx])
-        grad_norm, avg_loss, max_loss = m.tolist()
-        return {"train/grad_norm": grad_norm, "train/global_avg_loss": avg_loss, "train/global_max_loss": max_loss}
+        return fused_step_metrics(self.metrics[0], self.metrics[1], self.pg)
 
     def train_step(self, condition_model_conditions, latent_model_conditions, sigmas=None, noise=None,
                    sync_metrics=False):

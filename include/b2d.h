@@ -67,7 +67,7 @@ typedef struct {
   int32_t splits, batch;
   int64_t a_boff_row, a_boff_col, b_boff_row, b_boff_col, c_boff;  /* per-batch offsets (elements / rows / cols) */
   int32_t epi;
-  float alpha;
+  float alpha;               /* multiplies the accumulator; set it explicitly (1.0f for a plain product; 0 yields zeros) */
   void* out; int64_t ldc;
   void* out2; int64_t ldc2;
   const void* bias;                 /* bf16 [N] or NULL */

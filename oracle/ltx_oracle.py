@@ -492,11 +492,13 @@ def clip_grad_norm_(params, max_norm: float):
 
 
 def make_synthetic_batch(cfg: LTXConfig, B: int, Fr: int, H: int, W: int, text_len: int = 128, seed: int = 1234,
-                         dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
-    """SURVEY §8(d) synthetic inputs (already-normalised latents; ragged text masks)."""
+                         dtype=torch.bfloat16, text_scale: float = 0.1) -> Dict[str, torch.Tensor]:
+    """SURVEY §8(d) synthetic inputs (already-normalised latents; ragged text masks).  ``text_scale`` is the std of the
+    text embeddings: 0.1 is the survey's throughput setting; 1.0 (T5-like magnitudes) gives the cross-attention logits
+    an O(1) spread so that the attn2 q/k adapter gradients are well above bf16 rounding noise (parity tests use it)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     latents = torch.randn(B, cfg.in_channels, Fr, H, W, generator=g).to(dtype)
-    ehs = (torch.randn(B, text_len, cfg.caption_channels, generator=g) * 0.1).to(dtype)
+    ehs = (torch.randn(B, text_len, cfg.caption_channels, generator=g) * text_scale).to(dtype)
     lens = torch.randint(max(1, text_len // 8), text_len + 1, (B,), generator=g)
     mask = (torch.arange(text_len)[None, :] < lens[:, None])
     noise = torch.randn(B, cfg.in_channels, Fr, H, W, generator=g).to(dtype)

@@ -9,25 +9,36 @@ from _util import build_pair, run_b200_micro, SMALL, rel_err
 pytestmark = pytest.mark.gpu
 
 
+def lora_grad_errors(bm, om):
+    """{name: max|g_b200 - g_oracle| / max|g_oracle|} for every adapter tensor (per-tensor scale, no global floor)."""
+    og = dict(om.named_parameters())
+    errs = {}
+    for n, p in bm.named_parameters():
+        if "lora_" in n:
+            go = og[n].grad
+            assert go is not None and go.abs().max().item() > 0, n
+            errs[n] = (p.grad.float().cpu() - go).abs().max().item() / go.abs().max().item()
+    return errs
+
+
 @pytest.mark.parametrize("rank", [64, 16])
 def test_small_model_step_matches_oracle(rank):
     O, om, bm = build_pair(SMALL, rank)
-    batch = O.make_synthetic_batch(om.cfg, 2, 2, 4, 9, text_len=24, seed=7)  # S = 72: ragged vs the 128-row tiles
+    # S = 72: ragged vs the 128-row tiles.  text_scale=1.0: the cross-attention logits get an O(1) spread, so the attn2
+    # to_q/to_k adapter gradients are as large as the others (with the 0.1 throughput setting the text softmax is uniform
+    # and those gradients cancel to rounding noise) and EVERY adapter tensor is held to the same per-tensor bound.
+    batch = O.make_synthetic_batch(om.cfg, 2, 2, 4, 9, text_len=24, seed=7, text_scale=1.0)
     loss_o, pred_o = O.oracle_step(om, {k: (v.float() if v.is_floating_point() else v) for k, v in batch.items()})
     st, loss_b, pred_b = run_b200_micro(bm, batch)
     assert abs(loss_b - loss_o.item()) / abs(loss_o.item()) < 1e-3
     assert rel_err(pred_b, pred_o) < 3e-2
     og = dict(om.named_parameters())
-    # Gradient tolerance: 5 % of the parameter's own gradient scale, floored at 5 % of the global gradient scale.
-    # The floor matters only for the cross-attention q/k adapters: with synthetic weights the text softmax is nearly
-    # uniform, dS = P*(dP - delta) cancels to ~1e-7 (1000x below every other gradient) and ANY bf16 implementation --
-    # including the bf16-typed oracle, i.e. what the reference computes -- carries O(1) relative noise there.
+    errs = lora_grad_errors(bm, om)
     gmax = max(p.grad.abs().max().item() for n, p in om.named_parameters() if "lora_" in n)
-    for n, p in bm.named_parameters():
-        if "lora_" in n:
-            go = og[n].grad
-            e = (p.grad.float().cpu() - go).abs().max().item() / max(go.abs().max().item(), 5e-2 * gmax)
-            assert e < 5e-2, (n, e)
+    for n, e in errs.items():
+        # every adapter gradient is within 300x of the largest one (nothing is rounding noise), and within 5 % of ITS OWN scale
+        assert og[n].grad.abs().max().item() > gmax / 300, (n, og[n].grad.abs().max().item(), gmax)
+        assert e < 5e-2, (n, e)
     # optimizer step: matches torch AdamW + clip on the oracle's gradients
     params = [p for n, p in om.named_parameters() if "lora_" in n]
     O.clip_grad_norm_(params, 1.0)
@@ -38,6 +49,71 @@ def test_small_model_step_matches_oracle(rank):
     for n, p in bm.named_parameters():
         if "lora_" in n:
             assert (p.detach().float().cpu() - og[n].detach()).abs().max().item() < 2e-4, n
+
+
+@pytest.mark.timeout(600)
+def test_full_width_two_block_forward_backward_matches_oracle():
+    """BASELINE width (D=2048, H=32, S=2688 tokens = 21 full 128-row tiles, L=128 text keys, r=64), 2 blocks, B=1:
+    forward loss AND every LoRA gradient against the fp32 oracle.  This is the shape the step's dominant kernels run
+    at (gemm<160/256>, attn_fwd_db, attn_bwd_pp, attn_x*), which the S=72 small-model tests never reach."""
+    from oracle import ltx_oracle as O
+    cfgk = dict(num_layers=2)
+    O, om, bm = build_pair(cfgk, 64)
+    batch = O.make_synthetic_batch(om.cfg, 1, 7, 16, 24, seed=1234, text_scale=1.0)
+    loss_o, pred_o = O.oracle_step(om, {k: (v.float() if v.is_floating_point() else v) for k, v in batch.items()})
+    st, loss_b, pred_b = run_b200_micro(bm, batch)
+    assert abs(loss_b - loss_o.item()) / abs(loss_o.item()) < 1e-3
+    assert rel_err(pred_b, pred_o) < 3e-2
+    errs = lora_grad_errors(bm, om)
+    assert len(errs) == 2 * 16
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+    print("full-width grad errors (worst 4):", worst)
+    for n, e in errs.items():
+        # per-tensor relative bound, no global floor; cross-attention q/k adapters included
+        assert e < 5e-2, (n, e, worst)
+    # cosine similarity of the whole flat gradient
+    og = dict(om.named_parameters())
+    gb = torch.cat([p.grad.float().cpu().flatten() for n, p in bm.named_parameters() if "lora_" in n])
+    go = torch.cat([og[n].grad.flatten() for n, p in bm.named_parameters() if "lora_" in n])
+    assert torch.dot(gb, go) / (gb.norm() * go.norm()) > 0.999
+    assert abs(gb.norm() / go.norm() - 1) < 1e-2
+
+
+def test_twenty_step_trajectory_bounds_bf16_lora_operand_drift():
+    """The reference keeps the LoRA branch in fp32 under DDP (trainer.py:130-136); this engine keeps fp32 MASTER weights
+    and gradients but feeds bf16 copies of A/B to the tensor cores.  20 optimizer steps (lr 1e-3, clip, AdamW) on the
+    same data stream as the fp32 oracle bound what that costs: the per-step loss stays within the north_star's 1e-3
+    relative on every step, and the accumulated adapter update keeps direction and length."""
+    from finetrainers_b200.trainer import SFTTrainStep
+    O, om, bm = build_pair(SMALL, 64, seed=3)
+    st = SFTTrainStep(bm, flow_weighting_scheme="none", lr=1e-3, seed=5)
+    st.spec.first_frame_conditioning_p = 0.0
+    params = [p for n, p in om.named_parameters() if "lora_" in n]
+    opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.99), weight_decay=1e-4, eps=1e-8)
+    p0 = {n: p.detach().clone() for n, p in om.named_parameters() if "lora_" in n}
+    worst = 0.0
+    for i in range(20):
+        batch = O.make_synthetic_batch(om.cfg, 2, 2, 4, 9, text_len=24, seed=500 + i, text_scale=1.0)
+        cond = {"encoder_hidden_states": batch["encoder_hidden_states"].cuda(), "encoder_attention_mask": batch["encoder_attention_mask"].cuda()}
+        lat = {"latents": batch["latents"].cuda(), "latents_mean": batch["latents_mean"].cuda(), "latents_std": batch["latents_std"].cuda()}
+        st.micro_step(cond, lat, sigmas=batch["sigmas"].view(-1).cuda(), noise=batch["noise"].cuda())
+        torch.cuda.synchronize()
+        loss_b = st.loss_buf.item()
+        opt.zero_grad(set_to_none=True)
+        loss_o, _ = O.oracle_step(om, {k: (v.float() if v.is_floating_point() else v) for k, v in batch.items()})
+        rel = abs(loss_b - loss_o.item()) / abs(loss_o.item())
+        worst = max(worst, rel)
+        assert rel < 1e-3, (i, loss_b, loss_o.item(), rel)
+        O.clip_grad_norm_(params, 1.0)
+        opt.step()
+        st.optimizer_step()
+    torch.cuda.synchronize()
+    print("20-step worst relative loss difference:", worst)
+    og = dict(om.named_parameters())
+    db = torch.cat([(p.detach().float().cpu() - p0[n]).flatten() for n, p in bm.named_parameters() if "lora_" in n])
+    do = torch.cat([(og[n].detach() - p0[n]).flatten() for n, p in bm.named_parameters() if "lora_" in n])
+    assert torch.dot(db, do) / (db.norm() * do.norm()) > 0.98
+    assert abs(db.norm() / do.norm() - 1) < 0.03
 
 
 def test_small_model_through_finetrainers_style_loss():
@@ -178,7 +254,7 @@ def test_three_step_trajectory_first_frame_conditioning_and_lr_schedule():
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_factor_fn("linear", num_warmup_steps=2, num_training_steps=10))
     p0 = {n: p.detach().clone() for n, p in om.named_parameters() if "lora_" in n}
     for i in range(3):
-        batch = O.make_synthetic_batch(om.cfg, 2, 3, 4, 6, text_len=20, seed=300 + i)
+        batch = O.make_synthetic_batch(om.cfg, 2, 3, 4, 6, text_len=20, seed=300 + i, text_scale=1.0)
         cond = {"encoder_hidden_states": batch["encoder_hidden_states"].cuda(), "encoder_attention_mask": batch["encoder_attention_mask"].cuda()}
         lat = {"latents": batch["latents"].cuda(), "latents_mean": batch["latents_mean"].cuda(), "latents_std": batch["latents_std"].cuda()}
         st.micro_step(cond, lat, sigmas=batch["sigmas"].view(-1).cuda(), noise=batch["noise"].cuda())
@@ -200,13 +276,13 @@ def test_three_step_trajectory_first_frame_conditioning_and_lr_schedule():
         sched.step()
         st.optimizer_step()
     torch.cuda.synchronize()
-    # Adam normalises every element to ~+-lr, so elements whose gradient is rounding noise (the cross-attention q/k
-    # adapters, see test_small_model_step_matches_oracle) move by O(lr) in either implementation; compare the UPDATE
-    # vectors of the well-conditioned adapters by direction and length instead of element-wise.
+    # Adam normalises every element to ~+-lr, so an element whose gradient is near zero moves by O(lr) in either
+    # implementation; compare the UPDATE vector of every adapter tensor (cross-attention q/k included: the text
+    # embeddings are conditioned, see test_small_model_step_matches_oracle) by direction and length.
     og = dict(om.named_parameters())
     checked = 0
     for n, p in bm.named_parameters():
-        if "lora_" in n and not ("attn2.to_q" in n or "attn2.to_k" in n):
+        if "lora_" in n:
             db = (p.detach().float().cpu() - p0[n]).flatten()
             do = (og[n].detach() - p0[n]).flatten()
             if do.norm() == 0:
@@ -214,4 +290,4 @@ def test_three_step_trajectory_first_frame_conditioning_and_lr_schedule():
             cos = torch.dot(db, do) / (db.norm() * do.norm())
             assert cos > 0.95 and abs(db.norm() / do.norm() - 1) < 0.05, (n, cos.item(), (db.norm() / do.norm()).item())
             checked += 1
-    assert checked >= 20
+    assert checked >= 30

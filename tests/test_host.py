@@ -150,6 +150,116 @@ def test_precomputed_reader_follows_reference_layout(tmp_path):
     assert vals == [0, 1, 2, 3] and rd.requires_data
 
 
+def test_resolution_sampler_and_collate_follow_reference_protocol():
+    """data/sampler.py:6-58 + modeling_utils.py:156-181: bucket by the leader tensor's (F,H,W), release full buckets,
+    concatenate tensors along dim 0, pass the ignore-keys through from the first item."""
+    from finetrainers_b200.data import ResolutionSampler, collate
+    from finetrainers_b200.specification import LTXVideoModelSpecification
+    s = ResolutionSampler(batch_size=2, dim_keys={"latents": (2, 3, 4)})
+    mk = lambda f, v: ({"encoder_hidden_states": torch.full((1, 4, 8), float(v)), "encoder_attention_mask": torch.ones(1, 4, dtype=torch.bool)},
+                       {"latents": torch.full((1, 8, f, 2, 2), float(v)), "num_frames": f, "height": 2, "width": 2,
+                        "latents_mean": torch.zeros(1, 8), "latents_std": torch.ones(1, 8)})
+    s.consume(*mk(1, 0)); assert not s.is_ready
+    s.consume(*mk(3, 1)); assert not s.is_ready          # different resolution: another bucket
+    s.consume(*mk(1, 2)); assert s.is_ready
+    cond_b, lat_b = s.get_batch()
+    assert not s.is_ready and len(cond_b) == 2 and len(lat_b) == 2
+    spec = LTXVideoModelSpecification()
+    lat = spec.collate_latents(list(lat_b))
+    cond = spec.collate_conditions(list(cond_b))
+    assert lat["latents"].shape == (2, 8, 1, 2, 2) and lat["latents"][:, 0, 0, 0, 0].tolist() == [0.0, 2.0]
+    assert lat["num_frames"] == 1 and lat["latents_mean"].shape == (1, 8)   # ignore-keys: first item only
+    assert cond["encoder_hidden_states"].shape == (2, 4, 8)
+    assert collate([{"a": "x"}, {"a": "y"}]) == {"a": ["x", "y"]}
+    with pytest.raises(ValueError):
+        ResolutionSampler(1, {"latents": (2,)}).consume({"foo": torch.zeros(1)})
+    with pytest.raises(ValueError):
+        ResolutionSampler(1, {"latents": (2,), "x": (0,)}).consume({"latents": torch.zeros(1, 1, 1)}, {"x": torch.zeros(1)})
+
+
+def test_precomputed_once_reader_cycles_over_rank_slice(tmp_path):
+    """precomputation.py:348-382: infinite iterator over indices rank*per_rank + i."""
+    from finetrainers_b200.data import PrecomputedOnceReader, save_item
+    for i in range(4):
+        save_item({"latents": torch.full((1, 2), float(i))}, i, tmp_path, "latent")
+    rd = PrecomputedOnceReader(tmp_path, "latent", rank=1, world_size=2, device=None)
+    assert len(rd) == 2
+    it = iter(rd)
+    assert [int(next(it)["latents"][0, 0]) for _ in range(5)] == [2, 3, 2, 3, 2] and not rd.requires_data
+    with pytest.raises(ValueError):
+        PrecomputedOnceReader(tmp_path, "latent", rank=7, world_size=8)
+
+
+class _LoraConfig:
+    """Field-for-field what ``peft.LoraConfig(r=, lora_alpha=, init_lora_weights=, target_modules=)`` carries
+    (peft is not installed here)."""
+
+    def __init__(self, r, lora_alpha, init_lora_weights, target_modules):
+        self.r, self.lora_alpha, self.init_lora_weights, self.target_modules = r, lora_alpha, init_lora_weights, target_modules
+        self.lora_dropout = 0.0
+
+
+def test_trainer_prepare_call_sequence_replays_on_the_b200_module():
+    """Replays ``SFTTrainer._prepare_trainable_parameters`` / ``_prepare_for_training`` call for call
+    (trainer.py:95-216) against the drop-in module and backend: requires_grad_(False), add_adapter(LoraConfig(...)) with
+    the reference's default target regex (config.py:26), cast_training_params(fp32), get_mesh().ndim, prepare_model,
+    .to(device), trainable-parameter count, parameters() for the optimizer, zero_grad."""
+    from finetrainers_b200.model import B200LTXTransformer, LTXConfig
+    from finetrainers_b200.parallel import B200ParallelBackend
+    cfg = LTXConfig(in_channels=32, out_channels=32, num_attention_heads=2, attention_head_dim=64, cross_attention_dim=128,
+                    num_layers=2, caption_channels=64)
+    tr = B200LTXTransformer(cfg, torch.bfloat16, "cpu")
+    with torch.no_grad():
+        for p in tr.parameters():
+            p.normal_(0, 0.02)
+    be = B200ParallelBackend(device_type="cpu")
+    tr.requires_grad_(False)                                                      # utils.set_requires_grad([...], False)
+    rx = "(transformer_blocks|single_transformer_blocks).*(to_q|to_k|to_v|to_out.0)"
+    tr.add_adapter(_LoraConfig(r=16, lora_alpha=32, init_lora_weights=True, target_modules=rx))     # trainer.py:122-128
+    assert not be.data_sharding_enabled
+    for p in tr.parameters():                                                     # diffusers cast_training_params(fp32)
+        if p.requires_grad:
+            p.data = p.to(torch.float32)
+    assert not be.context_parallel_enabled and not be.tensor_parallel_enabled and not be.pipeline_parallel_enabled
+    mesh = be.get_mesh()
+    assert mesh.ndim == 1
+    for key in ("dp", "dp_cp", "dp_replicate", "dp_shard_cp", "pp", "cp", "tp"):  # every key the loop indexes
+        assert be.get_mesh()[key].ndim == 1
+    assert be.get_mesh()[("dp_replicate", "dp_shard_cp")].size() == 1
+    with pytest.raises(KeyError):
+        be.get_mesh()["nope"]
+    be.prepare_model(tr)
+    tr.prepare()
+    before = {k: v.clone() for k, v in tr.state_dict().items()}
+    tr.to("cpu")                                                                  # _move_components_to_device: no-op move
+    tr.to(dtype=torch.bfloat16)                                                   # a cast AFTER prepare(): must re-pack
+    assert tr._prepared
+    a1 = tr.transformer_blocks[0].attn1
+    assert a1.to_k.base_layer.weight.data_ptr() == tr._blk[0]["Wqkv"][128:].data_ptr()
+    assert a1.to_q.lora_A["default"].weight.dtype == torch.float32               # fp32 masters survive the cast
+    assert a1.to_q.lora_A["default"].weight.data_ptr() == tr._blk[0]["A_qkv"].data_ptr()
+    for k, v in tr.state_dict().items():
+        assert torch.equal(v.float(), before[k].float()), k
+    trainable = [p for p in tr.parameters() if p.requires_grad]
+    assert sum(p.numel() for p in trainable) == 2 * 8 * 2 * 16 * 128               # blocks * linears * (A + B) * r * d
+    assert tr.lora_scaling == 2.0 and tr.lora_rank == 16
+    opt = torch.optim.AdamW(trainable, lr=1e-3)
+    opt.zero_grad()                                                               # set_to_none: grads re-attach lazily
+    assert tr._attach_lora_grads()
+    sd = {k: torch.zeros_like(v) for k, v in tr.state_dict().items()}
+    tr.load_state_dict(sd)                                                        # in-place copy keeps the packed views
+    assert tr._blk[0]["Wqkv"].abs().max().item() == 0.0 and tr.lora_flat.abs().max().item() == 0.0
+    # list-form targets (peft suffix matching) select the same modules; anything else is refused loudly
+    tr2 = B200LTXTransformer(cfg, torch.bfloat16, "cpu")
+    tr2.add_adapter(_LoraConfig(8, 8, "gaussian", ["to_q", "to_k", "to_v", "to_out.0"]))
+    assert tr2.lora_rank == 8
+    tr3 = B200LTXTransformer(cfg, torch.bfloat16, "cpu")
+    with pytest.raises(NotImplementedError):
+        tr3.add_adapter(_LoraConfig(8, 8, True, ["to_q", "to_v"]))
+    with pytest.raises(NotImplementedError):
+        tr3.add_adapter(_LoraConfig(8, 8, True, ".*(to_q|to_k|to_v|to_out.0|proj)"))
+
+
 def test_lora_export_keys_and_values(tmp_path):
     """adapters export under diffusers/peft names and round-trip bit-exactly."""
     from safetensors.torch import load_file
