@@ -53,18 +53,31 @@ struct AttnFwdParams {
 };
 
 // ================================================================================================
-// forward, decoupled version: 64-wide key tiles, S DOUBLE-buffered in TMEM (2 x 64 columns + 64 for O = 192 -> 256
-// allocated) and P double-buffered in smem, TWO CTAs per SM.  The MMA warp issues S(j+2) as soon as the softmax warps
-// have drained S(j), so S(j+1) is already waiting when softmax(j) finishes: the softmax warps never sit in the
-// "P ready -> PV issue -> commit -> S ready" round trip (~1.5 us on B200); they only wait on MMAs issued two tiles earlier.
+// forward: 64-wide key tiles, S DOUBLE-buffered in TMEM (2 x 64 columns + 64 for O = 192 -> 256 allocated), TWO CTAs per
+// SM.  The MMA warp issues S(j+2) as soon as the softmax warps have drained S(j), so S(j+1) is already waiting when
+// softmax(j) finishes: the softmax warps never sit in the "P ready -> PV issue -> commit -> S ready" round trip; they
+// only wait on MMAs issued two tiles earlier.
 //     MMA     :  S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ...
 //     softmax :  [0]        [1]          [2]  ...          (back to back)
+// P never goes through shared memory: each thread packs its row of P to bf16 and writes it with tcgen05.st over the
+// first 32 columns of the S buffer it has just read (row-private, so no cross-thread hazard), and O += P V runs with the
+// A operand in TENSOR MEMORY.  At 64-wide tiles an SS-form P V re-reads 16 KB of P + 8 KB of V from shared memory per
+// 128 tensor cycles on top of the 16 KB of P stores - more than the 128 B/clk shared-memory port delivers; the TS form
+// leaves only K and V tiles and Q on that port.  (The tensor pipe executes in issue order: S(j+2), issued after PV(j),
+// overwrites the columns PV(j) reads only after PV(j) has consumed them.)
 // ================================================================================================
 constexpr int FDB_KV = 64;                                  // key rows per tile
 constexpr int FDB_STAGES = 4;
 constexpr int FDB_KV_BYTES = FDB_KV * HD * 2;               // 8 KB (K or V tile)
-constexpr int FDB_P_BYTES = TILE * FDB_KV * 2;              // 16 KB (one swizzled chunk)
-constexpr int FDB_SMEM = TILE_BYTES /*Q*/ + FDB_STAGES * 2 * FDB_KV_BYTES + 2 * FDB_P_BYTES + 256;  // 112.25 KB
+constexpr int FDB_SMEM = TILE_BYTES /*Q*/ + FDB_STAGES * 2 * FDB_KV_BYTES + 256;  // 80.25 KB
+
+// packs 32 fp32 values to 16 bf16x2 words and stores them to 16 TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_store_bf16x32(uint32_t taddr, const float (&v)[32]) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    tmem_st16(taddr, w);
+}
 
 __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __grid_constant__ AttnFwdParams p) {
     extern __shared__ uint8_t smem_fdb[];  // no static smem: the dynamic window starts 1024-aligned
@@ -72,8 +85,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* sQ = smem;
     uint8_t* sKV = sQ + TILE_BYTES;                         // stage s: K at +s*16K, V at +8K
-    uint8_t* sPall = sKV + FDB_STAGES * 2 * FDB_KV_BYTES;   // P[b] at + b*16K
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sPall + 2 * FDB_P_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + FDB_STAGES * 2 * FDB_KV_BYTES);
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;                  // [4]
     uint64_t* kv_empty = kv_full + FDB_STAGES;     // [4]
@@ -111,7 +123,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;  // S[b] at 64*b, O at 128
+    const uint32_t tmem = *tmem_slot;  // S[b] at 64*b (P[b] = bf16 pairs over its first 32 columns), O at 128
     const uint32_t tO = tmem + 128;
 
     if (warp == 0) {
@@ -148,16 +160,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
             if (n_kv > 1) issue_s(1);
             for (int j = 0; j < n_kv; ++j) {
                 const int st = j % FDB_STAGES;
-                mbar_wait(&p_full[j & 1], (uint32_t)((j >> 1) & 1));  // P(j) written, S[j&1] drained
+                mbar_wait(&p_full[j & 1], (uint32_t)((j >> 1) & 1));  // P(j) in TMEM, S[j&1] drained
                 tc_fence_after();
-                const uint32_t lp = sdesc_lo_kmajor(smem_u32(sPall + (j & 1) * FDB_P_BYTES));
+                const uint32_t tP = tmem + (j & 1) * 64;
                 const uint32_t lv = sdesc_lo_mnmajor(smem_u32(sKV + st * 2 * FDB_KV_BYTES + FDB_KV_BYTES));
 #pragma unroll
                 for (int k = 0; k < FDB_KV / 16; ++k)
-                    umma_f16_lo(tO, lp + k * SDESC_KSTEP_KMAJOR, lv + k * SDESC_KSTEP_MNMAJOR, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    umma_f16_ts_lo(tO, tP + k * TMEM_A_KSTEP, lv + k * SDESC_KSTEP_MNMAJOR, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&kv_empty[st]);
                 umma_commit(&pv_done[j & 1]);
-                if (j + 2 < n_kv) issue_s(j + 2);
+                if (j + 2 < n_kv) issue_s(j + 2);  // after PV(j) in issue order: it overwrites the columns PV(j) reads
             }
         }
     } else {
@@ -167,14 +179,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
         float m_run = -INFINITY, l_run = 0.f;
         const float* kb = p.key_bias ? p.key_bias + (long long)b * p.Sk : nullptr;
         for (int j = 0; j < n_kv; ++j) {
-            const uint32_t tS = tmem + (j & 1) * 64;
-            uint8_t* sP = sPall + (j & 1) * FDB_P_BYTES;
+            const uint32_t tS = tmem + (j & 1) * 64 + lane_off;
             mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
             tc_fence_after();
-            if (j >= 2) {  // P[j&1] was last read by PV(j-2)
-                mbar_wait(&pv_done[j & 1], (uint32_t)(((j - 2) >> 1) & 1));
-                tc_fence_after();
-            }
             const int kv0 = j * FDB_KV;
             const bool fast = (kb == nullptr) && (kv0 + FDB_KV <= p.Sk);
             bool done = false;
@@ -182,20 +189,20 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
                 // Optimistic pass against the running maximum.  No per-element max: every term is >= 0, so a term above 2^8
                 // forces the tile's row sum above 2^8 as well - the sum (needed anyway) is the overflow detector, at worst
                 // sending a harmless tile through the exact two-pass path.  scale/offset FMAs and the row-sum adds run as
-                // packed fp32 pairs (FFMA2 / FADD2): this loop is issue-bound.
+                // packed fp32 pairs (FFMA2 / FADD2).  Both 32-column halves are requested before the first is consumed.
                 uint64_t l01 = f2_pack(0.f, 0.f), l23 = l01;
                 const uint64_t nm2 = f2_pack(-m_run, -m_run), scale2 = f2_pack(p.scale_log2, p.scale_log2);
-                const uint32_t aPs = smem_u32(sP);
-#pragma unroll 1
-                for (int c = 0; c < FDB_KV / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(tS + lane_off + c * 32, v);
-                    tmem_ld_wait();
+                uint32_t v0[32], v1[32];
+                tmem_ld32(tS, v0);
+                tmem_ld32(tS + 32, v1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
                     float pv[32];
 #pragma unroll
                     for (int e = 0; e < 32; e += 4) {
-                        const float a0 = __uint_as_float(v[e]), a1 = __uint_as_float(v[e + 1]);
-                        const float a2 = __uint_as_float(v[e + 2]), a3 = __uint_as_float(v[e + 3]);
+                        const float a0 = __uint_as_float(c ? v1[e] : v0[e]), a1 = __uint_as_float(c ? v1[e + 1] : v0[e + 1]);
+                        const float a2 = __uint_as_float(c ? v1[e + 2] : v0[e + 2]), a3 = __uint_as_float(c ? v1[e + 3] : v0[e + 3]);
                         float x0, x1, x2, x3;
                         f2_unpack(f2_fma(f2_pack(a0, a1), scale2, nm2), x0, x1);
                         f2_unpack(f2_fma(f2_pack(a2, a3), scale2, nm2), x2, x3);
@@ -206,11 +213,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
                         l01 = f2_add(l01, f2_pack(pv[e], pv[e + 1]));
                         l23 = f2_add(l23, f2_pack(pv[e + 2], pv[e + 3]));
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        sts128(aPs + sw128_off(r, c * 4 + u), pack_bf16x2(pv[u * 8], pv[u * 8 + 1]),
-                               pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]), pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]),
-                               pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]));
+                    tmem_store_bf16x32(tS + c * 16, pv);
                 }
                 float l0, l1, l2, l3;
                 f2_unpack(l01, l0, l1);
@@ -219,28 +222,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
                 if (!__any_sync(0xffffffffu, !(l_tile <= 256.0f))) {  // negated compare: NaN / inf also take the exact path
                     l_run += l_tile;
                     done = true;
-                }
-            }
-            if (!done) {
-                float mx = -INFINITY;
-#pragma unroll 1
-                for (int c = 0; c < FDB_KV / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(tS + lane_off + c * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int col = kv0 + c * 32 + e;
-                        float x = __uint_as_float(v[e]) * p.scale_log2;
-                        if (kb) x += kb[min(col, p.Sk - 1)] * LOG2E;
-                        x = col < p.Sk ? x : -INFINITY;
-                        mx = fmaxf(mx, x);
-                    }
-                }
-                float m_use = m_run;
-                if (j == 0) {
-                    m_use = mx;
                 } else {
+                    // the optimistic P already overwrote S[:, 0:32): this buffer's scores are gone, so the exact path must
+                    // not re-read them.  Recover: keep what was loaded in registers (v0 / v1 still hold the raw scores).
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
+                    mx *= p.scale_log2;
+                    float m_use = m_run;
                     const bool need = (mx - m_run) > 8.0f;
                     if (__any_sync(0xffffffffu, need)) {
                         // O must be quiescent: P V(j-1) was issued after our p_full(j-1) arrival; wait for it to retire
@@ -258,36 +247,81 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
                             for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
                             tmem_st32(tO + lane_off + c * 32, v);
                         }
-                        tmem_st_wait();
+                    }
+                    m_run = m_use;
+                    float l0e = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        float pv[32];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            const float pe = fast_exp2(fmaf(__uint_as_float(c ? v1[e] : v0[e]), p.scale_log2, -m_use));
+                            pv[e] = pe;
+                            l0e += pe;
+                        }
+                        tmem_store_bf16x32(tS + c * 16, pv);
+                    }
+                    l_run += l0e;
+                    done = true;
+                }
+            }
+            if (!done) {
+                // exact two-pass path: first tile, key bias, ragged last tile
+                uint32_t v0[32], v1[32];
+                tmem_ld32(tS, v0);
+                tmem_ld32(tS + 32, v1);
+                tmem_ld_wait();
+                float x[64];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int e = 0; e < 64; ++e) {
+                    const int col = kv0 + e;
+                    float xe = __uint_as_float(e < 32 ? v0[e] : v1[e - 32]) * p.scale_log2;
+                    if (kb) xe += kb[min(col, p.Sk - 1)] * LOG2E;
+                    xe = col < p.Sk ? xe : -INFINITY;
+                    x[e] = xe;
+                    mx = fmaxf(mx, xe);
+                }
+                float m_use = m_run;
+                if (j == 0) {
+                    m_use = mx;
+                } else {
+                    const bool need = (mx - m_run) > 8.0f;
+                    if (__any_sync(0xffffffffu, need)) {
+                        mbar_wait(&pv_done[(j - 1) & 1], (uint32_t)(((j - 1) >> 1) & 1));
+                        tc_fence_after();
+                        if (need) m_use = mx;
+                        const float alpha = fast_exp2(m_run - m_use);
+                        l_run *= alpha;
+#pragma unroll 1
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t v[32];
+                            tmem_ld32(tO + lane_off + c * 32, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+                            tmem_st32(tO + lane_off + c * 32, v);
+                        }
                     }
                 }
                 m_run = m_use;
+                // a fully masked row keeps m = -inf: exponentiate against 0 then (every term is exp2(-inf) = 0)
+                const float m_sub = (m_use == -INFINITY) ? 0.f : m_use;
                 float l0 = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < FDB_KV / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(tS + lane_off + c * 32, v);
-                    tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
                     float pv[32];
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
-                        const int col = kv0 + c * 32 + e;
-                        float x = __uint_as_float(v[e]) * p.scale_log2 - m_use;
-                        if (kb) x += kb[min(col, p.Sk - 1)] * LOG2E;
-                        float pe = col < p.Sk ? fast_exp2(x) : 0.f;
+                        const float pe = fast_exp2(x[c * 32 + e] - m_sub);
                         pv[e] = pe;
                         l0 += pe;
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint4 w = make_uint4(pack_bf16x2(pv[u * 8], pv[u * 8 + 1]), pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]),
-                                             pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]), pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]));
-                        *reinterpret_cast<uint4*>(sP + sw128_off(r, c * 4 + u)) = w;
-                    }
+                    tmem_store_bf16x32(tS + c * 16, pv);
                 }
                 l_run += l0;
             }
-            fence_proxy_async_smem();
+            tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&p_full[j & 1]);
         }
@@ -373,22 +407,25 @@ struct AttnBwdParams {
 };
 
 // ================================================================================================
-// backward, pipelined version: ONE CTA per SM.  The S / dP accumulators are TRIPLE-buffered in TMEM (3 x 128 columns +
-// 128 columns of dV/dK or dQ accumulators = all 512), so the MMA warp runs up to three streamed tiles ahead of the two
-// consumer warpgroups, which alternate tiles.  The dependent chain  "consumer done -> MMA issue -> commit -> consumer"
-// costs ~1.5 us per hop-pair on B200 (measured: a kernel doing only these handshakes runs 290 us); what this design buys
-// is three such chains in flight per SM instead of two.
+// backward, pipelined: ONE CTA per SM.  The S / dP accumulators are TRIPLE-buffered in TMEM (3 x 128 columns + 128
+// columns of dV/dK or dQ accumulators = all 512), so the MMA warp runs up to three streamed tiles ahead of the two
+// consumer warpgroups, which alternate tiles.
 //     MMA :  SdP(0) SdP(1) SdP(2) | dVdK(0) SdP(3) | dVdK(1) SdP(4) | ...
 //     WG0 :  [exp,dS](0)      [exp,dS](2)      [exp,dS](4) ...
 //     WG1 :       [exp,dS](1)      [exp,dS](3) ...
+// P^T and dS^T never go through shared memory: each consumer thread packs its row to bf16 and writes it with tcgen05.st
+// over the first 32 columns of the S (resp. dP) buffer it has just read, and the dV / dK / dQ GEMMs take that A operand
+// from TENSOR MEMORY.  With smem-resident P^T/dS^T the dK/dV pass moved 136 KB per 64-row tile through the 128 B/clk
+// shared-memory port (ncu: tensor-side reads 53 % + load/store 46 % of its peak = saturated) for 512 tensor cycles of
+// work; the TS form leaves the 64 KB of K/V/Q/dO operand reads.  The tensor pipe executes in issue order, so SdP(it+3),
+// issued after dVdK(it), overwrites the columns dVdK(it) reads only after it has consumed them.
 // ================================================================================================
 constexpr int PP_TY = 64;
-constexpr int PP_STAGES = 5;                          // streamed (Y) tiles in flight
+constexpr int PP_STAGES = 6;                          // streamed (Y) tiles in flight
 constexpr int PP_NBUF = 3;                            // S/dP TMEM buffers
 constexpr int PP_THREADS = 320;                       // TMA warp, MMA warp, 2 x 4 consumer warps
 constexpr int PP_Y_BYTES = PP_TY * HD * 2;            // 8 KB
-constexpr int PP_PS_BYTES = TILE * PP_TY * 2;         // 16 KB
-constexpr int PP_SMEM = 2 * TILE_BYTES + PP_STAGES * 2 * PP_Y_BYTES + 2 * PP_NBUF * PP_PS_BYTES + PP_STAGES * 2 * PP_TY * 4 + 1024 + 256;
+constexpr int PP_SMEM = 2 * TILE_BYTES + PP_STAGES * 2 * PP_Y_BYTES + PP_STAGES * 2 * PP_TY * 4 + 1024 + 256;
 
 template <bool DKV>
 __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid_constant__ AttnBwdParams p) {
@@ -398,9 +435,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
     uint8_t* sX1 = smem;
     uint8_t* sX2 = sX1 + TILE_BYTES;
     uint8_t* sY = sX2 + TILE_BYTES;                         // stage s: Y1 at +s*2*Y_BYTES, Y2 right after
-    uint8_t* sP = sY + PP_STAGES * 2 * PP_Y_BYTES;          // P^T buffers [3] (one per accumulator buffer)
-    uint8_t* sDS = sP + PP_NBUF * PP_PS_BYTES;              // dS buffers [3]
-    float* sColA = reinterpret_cast<float*>(sDS + PP_NBUF * PP_PS_BYTES);  // [stages][TY]
+    float* sColA = reinterpret_cast<float*>(sY + PP_STAGES * 2 * PP_Y_BYTES);  // [stages][TY]
     float* sColD = sColA + PP_STAGES * TY;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sColD + PP_STAGES * TY);
     uint64_t* x_full = bars;
@@ -408,8 +443,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
     uint64_t* y_empty = y_full + PP_STAGES;        // [PP_STAGES]
     uint64_t* s_full = y_empty + PP_STAGES;        // [PP_NBUF]
     uint64_t* ds_full = s_full + PP_NBUF;          // [2]  (per warpgroup)
-    uint64_t* mm_done = ds_full + 2;               // [PP_NBUF] (per P/dS buffer)
-    uint64_t* all_done = mm_done + PP_NBUF;
+    uint64_t* all_done = ds_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -433,10 +467,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             mbar_init(&y_full[i], 1);
             mbar_init(&y_empty[i], 1);
         }
-        for (int i = 0; i < PP_NBUF; ++i) {
-            mbar_init(&s_full[i], 1);
-            mbar_init(&mm_done[i], 1);
-        }
+        for (int i = 0; i < PP_NBUF; ++i) mbar_init(&s_full[i], 1);
         for (int i = 0; i < 2; ++i) mbar_init(&ds_full[i], 128);
         mbar_init(all_done, 1);
         fence_mbar_init();
@@ -449,7 +480,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // S[k] at 128*k, dP[k] at 128*k + 64 (k = 0..2), out1 at 384, out2 at 448
+    // S[k] at 128*k (P^T[k] = bf16 pairs over its first 32 columns), dP[k] at 128*k + 64 (dS^T[k] likewise), k = 0..2;
+    // out1 at 384, out2 at 448
     const uint32_t tO1 = tmem + 384, tO2 = tmem + 448;
 
     if (warp == 0) {
@@ -499,30 +531,25 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             for (int it = 0; it < n_y; ++it) {
                 const int bsel = it & 1;
                 const int st = it % PP_STAGES;
-                mbar_wait(&ds_full[bsel], (uint32_t)((it >> 1) & 1));  // consumer finished tile it: P/dS ready, S/dP[it%3] free
+                mbar_wait(&ds_full[bsel], (uint32_t)((it >> 1) & 1));  // consumer finished tile it: P^T/dS^T in TMEM
                 tc_fence_after();
                 const uint32_t aY1 = smem_u32(sY + st * 2 * PP_Y_BYTES), aY2 = aY1 + PP_Y_BYTES;
-                const int kbuf = it % PP_NBUF;
-                const uint32_t aP = smem_u32(sP + kbuf * PP_PS_BYTES), aDS = smem_u32(sDS + kbuf * PP_PS_BYTES);
-                // refill the drained accumulator buffer first: S/dP(it+3) heads the consumers' chain, dV/dK(it) does not
-                // (P/dS are triple-buffered as well, so nothing downstream waits on dV/dK(it) soon)
-                if (it + PP_NBUF < n_y) issue_sdp(it + PP_NBUF);
+                const uint32_t tP = tmem + (it % PP_NBUF) * 128, tDS = tP + 64;
                 if (DKV) {
-                    const uint32_t lp = sdesc_lo_kmajor(aP), ly = sdesc_lo_mnmajor(aY2);
+                    const uint32_t ly = sdesc_lo_mnmajor(aY2);
 #pragma unroll
-                    for (int k = 0; k < TY / 16; ++k)  // out1 (dV) += P^T . dO_i   (Y2 as MN-major B)
-                        umma_f16_lo(tO1, lp + k * SDESC_KSTEP_KMAJOR, ly + k * SDESC_KSTEP_MNMAJOR, idesc_o,
-                                    (it > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < TY / 16; ++k)  // out1 (dV) += P^T . dO_i   (A in TMEM, Y2 as MN-major B)
+                        umma_f16_ts_lo(tO1, tP + k * TMEM_A_KSTEP, ly + k * SDESC_KSTEP_MNMAJOR, idesc_o, (it > 0 || k > 0) ? 1u : 0u);
                 }
                 {
-                    const uint32_t ld = sdesc_lo_kmajor(aDS), ly = sdesc_lo_mnmajor(aY1);
+                    const uint32_t ly = sdesc_lo_mnmajor(aY1);
 #pragma unroll
-                    for (int k = 0; k < TY / 16; ++k)  // out2 += dS . Y1   (Y1 as MN-major B)
-                        umma_f16_lo(tO2, ld + k * SDESC_KSTEP_KMAJOR, ly + k * SDESC_KSTEP_MNMAJOR, idesc_o,
-                                    (it > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < TY / 16; ++k)  // out2 += dS . Y1   (A in TMEM, Y1 as MN-major B)
+                        umma_f16_ts_lo(tO2, tDS + k * TMEM_A_KSTEP, ly + k * SDESC_KSTEP_MNMAJOR, idesc_o, (it > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&y_empty[st]);
-                umma_commit(&mm_done[kbuf]);
+                // refill the buffer only now: S/dP(it+3) overwrite the columns the two GEMMs above read (issue order)
+                if (it + PP_NBUF < n_y) issue_sdp(it + PP_NBUF);
             }
             umma_commit(all_done);
         }
@@ -547,10 +574,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             const int i = y0 + it;
             const int st = it % PP_STAGES;
             const int kb = it % PP_NBUF;
-            const int t = it >> 1;  // this warpgroup's own tile counter
-            const uint32_t tS = tmem + kb * 128, tDP = tS + 64;
-            uint8_t* myP = sP + kb * PP_PS_BYTES;
-            uint8_t* myDS = sDS + kb * PP_PS_BYTES;
+            const uint32_t tS = tmem + kb * 128 + lane_off, tDP = tS + 64;
             float* cA = sColA + st * TY;
             float* cD = sColD + st * TY;
             const bool full_tile = (i + 1) * TY <= rowsY;
@@ -573,18 +597,14 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             if (col_by_copy) mbar_wait(&y_full[st], (uint32_t)((it / PP_STAGES) & 1));
             mbar_wait(&s_full[kb], (uint32_t)((it / PP_NBUF) & 1));
             tc_fence_after();
-            if (it >= PP_NBUF) {  // P/dS buffer kb was last read by the dV/dK MMAs of tile it-3
-                mbar_wait(&mm_done[kb], (uint32_t)(((it / PP_NBUF) - 1) & 1));
-                tc_fence_after();
-            }
-            const uint32_t aP = smem_u32(myP), aDS = smem_u32(myDS), aCA = smem_u32(cA), aCD = smem_u32(cD);
+            const uint32_t aCA = smem_u32(cA), aCD = smem_u32(cD);
             // the per-row term is only non-trivial with a key bias or a ragged X tile (DKV), resp. it carries -lse (dQ pass)
             const bool add_row = !DKV || p.key_bias != nullptr || !row_ok;
 #pragma unroll 1
             for (int c = 0; c < TY / 32; ++c) {
                 uint32_t sv[32], dv[32];
-                tmem_ld32(tS + lane_off + c * 32, sv);
-                tmem_ld32(tDP + lane_off + c * 32, dv);
+                tmem_ld32(tS + c * 32, sv);
+                tmem_ld32(tDP + c * 32, dv);
                 float pe[32], ds[32];
                 const uint64_t scale2 = f2_pack(p.scale_log2, p.scale_log2);
                 if (no_col) {
@@ -627,17 +647,12 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
                         f2_unpack(f2_mul(f2_pack(pe[e], pe[e + 1]), t2), ds[e], ds[e + 1]);
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t off = sw128_off(r, c * 4 + u);
-                    if (DKV)
-                        sts128(aP + off, pack_bf16x2(pe[u * 8], pe[u * 8 + 1]), pack_bf16x2(pe[u * 8 + 2], pe[u * 8 + 3]),
-                               pack_bf16x2(pe[u * 8 + 4], pe[u * 8 + 5]), pack_bf16x2(pe[u * 8 + 6], pe[u * 8 + 7]));
-                    sts128(aDS + off, pack_bf16x2(ds[u * 8], ds[u * 8 + 1]), pack_bf16x2(ds[u * 8 + 2], ds[u * 8 + 3]),
-                           pack_bf16x2(ds[u * 8 + 4], ds[u * 8 + 5]), pack_bf16x2(ds[u * 8 + 6], ds[u * 8 + 7]));
-                }
+                // chunk c's bf16 pairs land in columns [16 c, 16 c + 16) of the S (resp. dP) buffer: columns this thread
+                // has already read (chunk 0) or that hold chunk-0 values consumed above (chunk 1)
+                if (DKV) tmem_store_bf16x32(tS + c * 16, pe);
+                tmem_store_bf16x32(tDP + c * 16, ds);
             }
-            fence_proxy_async_smem();
+            tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&ds_full[wg]);
         }

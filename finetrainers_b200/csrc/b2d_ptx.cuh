@@ -317,6 +317,22 @@ __device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t alo, uint3
         "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(SDESC_HI_SW128)
         : "memory");
 }
+// A operand read from TENSOR MEMORY (row m of A = TMEM lane m; 16-bit elements packed two per 32-bit column, so one
+// K = 16 step spans 8 columns), B from shared memory.  Used by the attention kernels for O += P V, dV += P^T dO,
+// dK += dS^T Q, dQ += dS K: P / dS never touch shared memory (whose 128 B/clk port the SS form saturates at N = 64).
+__device__ __forceinline__ void umma_f16_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(blo), "r"(idesc), "r"(accumulate), "r"(SDESC_HI_SW128)
+        : "memory");
+}
+constexpr uint32_t TMEM_A_KSTEP = 8;  // 16 bf16 of K = 8 columns
 // same, issued by the pair's leader CTA for both CTAs (M = 256: 128 accumulator rows in each CTA's TMEM)
 __device__ __forceinline__ void umma_f16_lo_2sm(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -369,6 +385,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
         "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
         "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
 

@@ -37,8 +37,12 @@ def test_reference_attention_kat_through_provider_hook():
 
 @pytest.mark.parametrize("B,H,Sq,Sk,bias", [(1, 32, 2688, 2688, False), (2, 4, 2688, 128, True), (1, 2, 200, 72, True),
                                             (1, 2, 128, 128, False), (1, 3, 1, 1, False), (2, 2, 130, 257, True),
-                                            (1, 32, 2688, 128, True), (5, 32, 300, 128, True), (3, 2, 1000, 100, False)])
+                                            (1, 32, 2688, 128, True), (5, 32, 300, 128, True), (3, 2, 1000, 100, False),
+                                            (1, 2, 1000, 300, True), (1, 1, 640, 512, False)])
 def test_attention_fwd_bwd_shapes(B, H, Sq, Sk, bias):
+    """Covers every dispatch branch of b2d_attn_fwd / b2d_attn_bwd: long keys (fwd_db + bwd_pp, full and ragged tiles,
+    with and without key bias), one key tile (attn_x*, one or several query ranges per head), and 128 < Sk <= 512 with
+    few heads (the dK/dV pass split over gridDim.z with fp32 atomics: the last two cases)."""
     from finetrainers_b200 import ops
     torch.manual_seed(0)
     q, k, v = rnd(B, H, Sq, 64), rnd(B, H, Sk, 64), rnd(B, H, Sk, 64)
