@@ -120,6 +120,25 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # reference arm: the CPU restatement of the reference step on the host cores
 # ----------------------------------------------------------------------------------------------------------------------
+def physical_cores():
+    """Physical cores this process may run on (SMT siblings counted once): oversubscribing the hyperthreads made the
+    fp32 oracle ~10x slower on the 128-thread GPU hosts."""
+    try:
+        allowed = os.sched_getaffinity(0)
+        seen, cur = set(), {}
+        for line in open("/proc/cpuinfo"):
+            if ":" in line:
+                k, v = [x.strip() for x in line.split(":", 1)]
+                cur[k] = v
+            elif not line.strip() and cur:
+                if int(cur.get("processor", -1)) in allowed:
+                    seen.add((cur.get("physical id", "0"), cur.get("core id", cur.get("processor"))))
+                cur = {}
+        return max(1, len(seen)) if seen else max(1, len(allowed) // 2)
+    except Exception:  # noqa: BLE001
+        return max(1, (os.cpu_count() or 2) // 2)
+
+
 class CpuReference:
     """Oracle (fp32) with `layers` of the 28 blocks at full width (D=2048, S=2688, L=128, r=64, B=1); one sample = one
     forward + loss + backward.  Built once, sampled many times."""
@@ -128,7 +147,7 @@ class CpuReference:
         import torch
         from oracle import ltx_oracle as O
         # torchrun exports OMP_NUM_THREADS=1; this leg runs on rank 0 alone, so it takes every core the box gives us
-        n = threads or len(os.sched_getaffinity(0)) or os.cpu_count()
+        n = threads or physical_cores()
         torch.set_num_threads(n)
         self.cores = torch.get_num_threads()
         self.layers = layers
@@ -420,7 +439,7 @@ def run_b200(args):
         roof["algorithmic_bytes"] = tj.get("algorithmic_bytes")
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        ref = CpuReference(8)
+        ref = CpuReference(4)
         ref.sample()
         t = ref.sample()
         full = t * N_BLOCKS / ref.layers

@@ -441,28 +441,33 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 }
 
 // ================================================================================================
-// CTA-pair variant (EXPERIMENTAL, opt-in with B2D_GEMM_2CTA=1; not yet run on hardware - see DESIGN.md section 9).
-// The 1-CTA kernel above is bound by operand delivery: every SM ingests a full 256-row B tile per k-block.  Here two CTAs
-// of a 2-CTA cluster share one 256 x 256 tile: each stages its own 128 rows of A and its own 128 rows (half) of B, the
-// pair's leader issues one tcgen05.mma.cta_group::2 (M = 256) that reads both halves, and each CTA's TMEM receives its
-// 128 accumulator rows - per-SM ingest per k-block drops from 48 KB to 32 KB.  A is K-major, BN = 256, no split-K.
+// CTA-pair variant (cta_group::2).  The 1-CTA kernel above is bound by operand delivery: every SM ingests a full BN-row
+// B tile per k-block.  Here the two CTAs of a 2-CTA cluster (one TPC) share one 256 x BN tile: each stages its own 128
+// rows of A and its own HALF of B (BN/2 rows), the pair's leader issues one tcgen05.mma.cta_group::2 (M = 256) that reads
+// both halves, and each CTA's TMEM receives its 128 accumulator rows - per-SM ingest per k-block drops from
+// (128 + BN) to (128 + BN/2) rows.  Measured on B200 (tools/gemm_variants.py): FFN-up 84.1 -> 76.6 us, QKV 58.6 -> 53.3 us,
+// dX(W2) 78.3 -> 70.0 us.  A is K-major, no split-K.
 //   barriers: full (leader only; both CTAs' TMA loads credit it) / empty (one multicast commit arrival in each CTA) /
 //             tmem-full (multicast commit) / tmem-empty (leader only; 256 + 256 arrivals, the peer's arrive remotely)
 // ================================================================================================
-template <int B_MN>
+template <int BN_, int B_MN>
 struct Gemm2Cfg {
-    static constexpr int BN = 256;
-    static constexpr int B_STAGE_BYTES = (BN / 2) * BLOCK_K * 2;   // this CTA's half of B: 16 KB in either majorness
+    static constexpr int BN = BN_;
+    static constexpr int HALF = BN / 2;                            // B rows (columns of C) staged by one CTA
+    // K-major B: one [HALF x 64] box.  MN-major B: ceil(HALF/64) boxes of [64 k-rows x 64 n]
+    static constexpr int B_STAGE_BYTES = B_MN ? ((HALF + 63) / 64) * 8192 : HALF * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = 6;
-    static constexpr int TMEM_COLS = 512;
+    static constexpr int TX_BYTES = A_STAGE_BYTES + (B_MN ? ((HALF + 63) / 64) * 8192 : HALF * BLOCK_K * 2);
+    static constexpr int STAGES = (216 * 1024 / STAGE_BYTES) > 8 ? 8 : (216 * 1024 / STAGE_BYTES);
+    static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int B_MN>
+template <int BN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm2_kernel(const __grid_constant__ GemmKParams p) {
-    using Cfg = Gemm2Cfg<B_MN>;
-    constexpr int BN = Cfg::BN;
+    using Cfg = Gemm2Cfg<BN, B_MN>;
+    constexpr int HALF = Cfg::HALF;
+    constexpr int NBOX = (HALF + 63) / 64;  // MN-major B: 64-column boxes per CTA
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -518,12 +523,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm2_kernel(const __grid_con
                 const int t = w / m_pairs;
                 const int nt = t % p.n_tiles, z = t / p.n_tiles;
                 const int m0 = (2 * mp + rank) * BLOCK_M;          // this CTA's 128 rows of the 256-row pair tile
-                const int n0t = nt * BN, n0 = n0t + rank * (BN / 2);  // this CTA's half of the B tile
+                const int n0t = nt * BN, n0 = n0t + rank * HALF;      // this CTA's half of the B tile
                 for (int i = 0; i < nkb; ++i) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sB = sA + A_STAGE_BYTES;
-                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes land here
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::TX_BYTES);  // both CTAs' bytes land here
                     if (i < p.kb_main) {
                         const int k0 = i * BLOCK_K;
                         tma_load_2d_2sm(sA, &p.tmA, &full_bar[stage], k0 + z * p.a_bcol, m0 + z * p.a_brow);
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm2_kernel(const __grid_con
                             tma_load_2d_2sm(sB, &p.tmB, &full_bar[stage], k0 + z * p.b_bcol, n0 + z * p.b_brow);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < BN / 128; ++j)
+                            for (int j = 0; j < NBOX; ++j)
                                 tma_load_2d_2sm(sB + j * 8192, &p.tmB, &full_bar[stage], n0 + 64 * j + z * p.b_bcol,
                                                 k0 + z * p.b_brow);
                         }
@@ -543,7 +548,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm2_kernel(const __grid_con
                             tma_load_2d_2sm(sB, &p.tmB2, &full_bar[stage], k2, n0 + z * p.b2_brow);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < BN / 128; ++j)
+                            for (int j = 0; j < NBOX; ++j)
                                 tma_load_2d_2sm(sB + j * 8192, &p.tmB2, &full_bar[stage], n0 + 64 * j, k2 + z * p.b2_brow);
                         }
                     }
@@ -647,13 +652,13 @@ static int launch_gemm(const GemmKParams& kp, int grid, cudaStream_t stream) {
     return B2D_OK;
 }
 
-template <int B_MN>
+template <int BN, int B_MN>
 static int launch_gemm2(const GemmKParams& kp, int clusters, cudaStream_t stream) {
-    using Cfg = Gemm2Cfg<B_MN>;
+    using Cfg = Gemm2Cfg<BN, B_MN>;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    auto kern = gemm2_kernel<B_MN>;
+    auto kern = gemm2_kernel<BN, B_MN>;
     if (dev < 64 && !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return set_error(B2D_ERR_CUDA, "cudaFuncSetAttribute(gemm2): %s", cudaGetErrorString(e));
@@ -677,30 +682,47 @@ static int dispatch_major(const GemmKParams& kp, int a_mn, int b_mn, int grid, c
     return launch_gemm<BN, 1, 0>(kp, grid, s);
 }
 
-static int pick_block_n(int M, int N, int nsm, int work_mult, int a_mn, int b_mn, int group_n) {
-    // minimise (waves * tile cost) over the candidate tile widths; cost ~ BN + fixed overhead.
-    // 160 exists to beat wave quantisation at N = 2048 (13 x 21 = 273 tiles on 2 x 148 slots); MN-major B tiles are
-    // built from 64-column TMA boxes, so they need BN % 64 == 0.
+// Tile choice: minimise (waves x per-wave tile time) over tile widths and over the two schedulings.
+//   1-CTA tiles (128 x bn): per k-block a CTA ingests 128 + bn operand rows; per-wave cost ~ (128 + bn) + 16.
+//   pair tiles (256 x bn): each CTA ingests 128 + bn/2 rows and the pair occupies two SMs; measured on B200 a 256-wide
+//   pair tile costs ~0.9 of the 1-CTA 128 x 256 tile per wave (FFN-up 76.6 vs 84.1 us at equal wave counts), i.e.
+//   (128 + bn) * 0.9 + 16 - but N = 2048 leaves 88 pair tiles for 74 clusters (2 waves), where 1-CTA bn = 160 wins.
+// 160 exists to beat wave quantisation at N = 2048 (13 x 21 = 273 tiles on 2 x 148 slots); MN-major A tiles are built
+// from 64-column TMA boxes, so they need bn % 64 == 0.  Returns bn; *pair is set to 1 for CTA pairs.
+static int pick_tile(int M, int N, int nsm, int work_mult, int a_mn, int group_n, bool pair_ok, int force_pair, int* pair) {
     const int cands[5] = {256, 192, 160, 128, 64};
-    int best = 128;
+    int best = 128, best_pair = 0;
     double best_t = 1e30;
-    int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-    for (int i = 0; i < 5; ++i) {
-        int bn = cands[i];
-        if (a_mn && (bn % 64) != 0) continue;
-        if (group_n > 0 && (group_n % bn) != 0) continue;
-        if (bn > N && bn != 64) continue;
-        int n_tiles = (N + bn - 1) / bn;
-        long long tiles = (long long)m_tiles * n_tiles * work_mult;
-        long long waves = (tiles + nsm - 1) / nsm;
-        // per-k-block tile time is bounded by operand delivery, ~(128 + bn) rows of 128 B per k-block (measured on B200:
-        // at bn=128 the 1-CTA tile is L2->smem bound, at bn=256 MMA and delivery balance); + a fixed epilogue/fill term
-        double t = (double)waves * ((128 + bn) + 16);
-        if (t < best_t - 1e-9) {
-            best_t = t;
-            best = bn;
+    const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    for (int mode = 0; mode < 2; ++mode) {
+        if (mode == 1 && (!pair_ok || force_pair == 1)) continue;
+        if (mode == 0 && force_pair == 2 && pair_ok) continue;
+        for (int i = 0; i < 5; ++i) {
+            const int bn = cands[i];
+            if (a_mn && (bn % 64) != 0) continue;
+            if (group_n > 0 && (group_n % bn) != 0) continue;
+            if (bn > N && bn != 64) continue;
+            if (mode == 1 && bn == 64) continue;
+            const int n_tiles = (N + bn - 1) / bn;
+            double t;
+            if (mode == 0) {
+                const long long tiles = (long long)m_tiles * n_tiles * work_mult;
+                const long long waves = (tiles + nsm - 1) / nsm;
+                t = (double)waves * ((128 + bn) + 16);
+            } else {
+                const long long pairs = (long long)((m_tiles + 1) / 2) * n_tiles * work_mult;
+                const long long slots = nsm / 2;
+                const long long waves = (pairs + slots - 1) / slots;
+                t = (double)waves * ((128 + bn) * 0.9 + 16);
+            }
+            if (t < best_t - 1e-9) {
+                best_t = t;
+                best = bn;
+                best_pair = mode;
+            }
         }
     }
+    *pair = best_pair;
     return best;
 }
 
@@ -733,15 +755,31 @@ extern "C" int b2d_gemm(const b2d_gemm_desc* d, void* stream_v) {
     int nsm = device_sm_count();
     if (nsm <= 0) return B2D_ERR_CUDA;
     int max_ctas = d->max_ctas > 0 ? d->max_ctas : nsm;
-    int bn = d->block_n > 0 ? d->block_n : pick_block_n(d->M, d->N, max_ctas, splits * batch, d->a_mn_major, d->b_mn_major, d->a2_group_n);
+    if (d->cta_pair < 0 || d->cta_pair > 2) return set_error(B2D_ERR_ARG, "gemm: cta_pair must be 0 (auto), 1 or 2");
+    // CTA pairs need a K-major A operand, no split-K, at least one full pair of M tiles and two SMs
+    const bool pair_ok = !d->a_mn_major && splits == 1 && d->M > BLOCK_M && max_ctas >= 2;
+    if (d->cta_pair == 2 && !pair_ok)
+        return set_error(B2D_ERR_ARG, "gemm: cta_pair = 2 needs K-major A, splits = 1, M > 128 and max_ctas >= 2");
+    int pair = 0;
+    int bn;
+    if (d->block_n > 0) {
+        bn = d->block_n;
+        pair = d->cta_pair == 2 ? 1 : 0;
+        if (d->cta_pair == 0 && pair_ok && bn >= 128) {  // explicit width, automatic scheduling: compare the two at this width
+            const int m_tiles = (d->M + BLOCK_M - 1) / BLOCK_M, n_tiles = (d->N + bn - 1) / bn;
+            const long long t1 = ((long long)m_tiles * n_tiles * batch + max_ctas - 1) / max_ctas;
+            const long long t2 = ((long long)((m_tiles + 1) / 2) * n_tiles * batch + max_ctas / 2 - 1) / (max_ctas / 2);
+            pair = (double)t2 * ((128 + bn) * 0.9 + 16) < (double)t1 * ((128 + bn) + 16) ? 1 : 0;
+        }
+    } else {
+        bn = pick_tile(d->M, d->N, max_ctas, splits * batch, d->a_mn_major, d->a2_group_n, pair_ok, d->cta_pair, &pair);
+    }
     if (bn != 64 && bn != 128 && bn != 160 && bn != 192 && bn != 256) return set_error(B2D_ERR_ARG, "gemm: bad block_n %d", bn);
     if ((bn % 64) && d->a_mn_major) return set_error(B2D_ERR_ARG, "gemm: block_n 160 needs a K-major A operand");
+    if (pair && bn == 64) return set_error(B2D_ERR_ARG, "gemm: CTA pairs need block_n >= 128");
     if (d->a2_group_n > 0 && (d->a2_group_n % bn) != 0)
         return set_error(B2D_ERR_ARG, "gemm: a2_group_n (%d) must be a multiple of block_n (%d)", d->a2_group_n, bn);
-
-    // CTA-pair kernel (experimental, opt-in): 256-wide tiles of a K-major-A GEMM with at least one full pair of M tiles
-    static const bool two_cta_on = []() { const char* e = getenv("B2D_GEMM_2CTA"); return e && e[0] == '1'; }();
-    const bool two_cta = two_cta_on && !d->a_mn_major && bn == 256 && splits == 1 && d->M > BLOCK_M && max_ctas >= 2;
+    const bool two_cta = pair != 0;
     const int b_box_rows = two_cta ? bn / 2 : bn;  // K-major B: rows of the box one CTA loads
 
     GemmKParams kp;
@@ -811,7 +849,12 @@ extern "C" int b2d_gemm(const b2d_gemm_desc* d, void* stream_v) {
     if (two_cta) {
         const long long pairs = (long long)((kp.m_tiles + 1) / 2) * kp.n_tiles * batch;
         const int clusters = (int)(pairs < max_ctas / 2 ? pairs : max_ctas / 2);
-        return d->b_mn_major ? launch_gemm2<1>(kp, clusters, stream) : launch_gemm2<0>(kp, clusters, stream);
+        switch (bn) {
+            case 128: return d->b_mn_major ? launch_gemm2<128, 1>(kp, clusters, stream) : launch_gemm2<128, 0>(kp, clusters, stream);
+            case 160: return d->b_mn_major ? launch_gemm2<160, 1>(kp, clusters, stream) : launch_gemm2<160, 0>(kp, clusters, stream);
+            case 192: return d->b_mn_major ? launch_gemm2<192, 1>(kp, clusters, stream) : launch_gemm2<192, 0>(kp, clusters, stream);
+            default: return d->b_mn_major ? launch_gemm2<256, 1>(kp, clusters, stream) : launch_gemm2<256, 0>(kp, clusters, stream);
+        }
     }
 
     switch (bn) {

@@ -45,6 +45,7 @@ class GemmDesc(C.Structure):
         ("block_n", C.c_int32),
         ("max_ctas", C.c_int32),
         ("a2_boff_row", C.c_int64), ("b2_boff_row", C.c_int64), ("bias_boff", C.c_int64),
+        ("cta_pair", C.c_int32),
     ]
 
 

@@ -64,7 +64,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          a_boff=(0, 0), b_boff=(0, 0), c_boff=0, epi=EPI_STORE, alpha=1.0, out2=None, ldc2=None, bias=None, res=None,
          ldres=None, aux=None, ldaux=None, gate_table=None, gate_temb=None, gate2_table=None, gate2_temb=None,
          temb_stride=0, rows_per_sample=0, block_n=0, max_ctas=0, a2_boff_row=0, b2_boff_row=0, bias_boff=0,
-         tag="gemm"):
+         cta_pair=0, tag="gemm"):
     """C = epilogue(alpha * (opA(A) opB(B)^T + A2 B2^T)).  See include/b2d.h b2d_gemm_desc."""
     d = GemmDesc()
     d.A = A.data_ptr(); d.lda = lda if lda is not None else A.stride(0)
@@ -99,6 +99,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     d.block_n = block_n
     d.max_ctas = max_ctas
     d.a2_boff_row, d.b2_boff_row, d.bias_boff = a2_boff_row, b2_boff_row, bias_boff
+    d.cta_pair = cta_pair
     with _Timed(tag):
         check(_l.load().b2d_gemm(C.byref(d), _stream()), "gemm")
     _count()

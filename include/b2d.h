@@ -79,11 +79,14 @@ typedef struct {
   const void* gate2_temb;
   int64_t temb_stride;
   int32_t rows_per_sample;          /* b = row / rows_per_sample */
-  int32_t block_n;                  /* 0 = auto; else 64/128/192/256 */
+  int32_t block_n;                  /* 0 = auto; else 64/128/160/192/256 */
   int32_t max_ctas;                 /* 0 = #SMs */
   /* batch offsets of the extension operands and of the bias (batch z reads A2 rows + z*a2_boff_row, B2 rows
    * + z*b2_boff_row, bias + z*bias_boff elements): one launch covers the same projection of several DiT blocks */
   int64_t a2_boff_row, b2_boff_row, bias_boff;
+  /* tile scheduling across CTAs: 0 = auto (cost model), 1 = one CTA per 128 x block_n tile, 2 = CTA pairs sharing a
+   * 256 x block_n tile (tcgen05 cta_group::2; needs K-major A, no split-K, block_n in 128/160/192/256, M > 128) */
+  int32_t cta_pair;
 } b2d_gemm_desc;
 
 int b2d_gemm(const b2d_gemm_desc* d, void* stream);

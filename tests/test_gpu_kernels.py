@@ -30,6 +30,29 @@ def test_gemm_kmajor(ops, M, N, K, bn):
     assert rel_err(out, A.float() @ B.float().t()) < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K,bn,b_mn", [(2688, 2048, 2048, 256, False), (2688, 2048, 512, 160, False), (300, 520, 200, 192, False),
+                                           (2688, 1024, 256, 128, False), (2688, 2048, 512, 256, True), (700, 2048, 512, 160, True),
+                                           (2688, 768, 200, 192, True), (129, 128, 64, 128, True)])
+def test_gemm_cta_pairs(ops, M, N, K, bn, b_mn):
+    """tcgen05 cta_group::2 tiles (two CTAs share a 256 x bn tile) at every supported width, both B layouts, ragged M
+    (an odd number of 128-row tiles leaves the last pair half empty), ragged N and K tails, bias + LoRA extension."""
+    torch.manual_seed(0)
+    A = rnd(M, K)
+    Bm = rnd(K, N, scale=0.05) if b_mn else rnd(N, K, scale=0.05)
+    bias = rnd(N)
+    u = rnd(M, 64, scale=0.3)
+    Bl = rnd(64, N, scale=0.05) if b_mn else rnd(N, 64, scale=0.05)
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, Bm, out, M=M, N=N, K=K, b_mn=b_mn, bias=bias, A2=u, B2=Bl, K2=64, block_n=bn, cta_pair=2)
+    ref = A.float() @ (Bm.float() if b_mn else Bm.float().t()) + bias.float() + u.float() @ (Bl.float() if b_mn else Bl.float().t())
+    assert rel_err(out, ref) < 1e-2
+    out1 = torch.zeros_like(out)
+    ops.gemm(A, Bm, out1, M=M, N=N, K=K, b_mn=b_mn, bias=bias, A2=u, B2=Bl, K2=64, block_n=bn, cta_pair=1)
+    assert rel_err(out1, ref) < 1e-2
+    with pytest.raises(Exception):
+        ops.gemm(A[:64], Bm, out, M=64, N=N, K=K, b_mn=b_mn, block_n=bn, cta_pair=2)   # one M tile: no pair
+
+
 @pytest.mark.parametrize("M,N,K", [(256, 128, 128), (2688, 2048, 8192), (200, 192, 136)])
 def test_gemm_b_mn_major(ops, M, N, K):
     torch.manual_seed(0)
