@@ -37,11 +37,11 @@ N_BLOCKS = 28
 FLOP_PER_TOKEN_ALG = 8.88e9              # 2G + 3.5A, no recompute counted
 
 
-def workload_config(B, world):
+def workload_config(B, world, parallelism="ddp"):
     """The `config` object of BOTH arms (the reference arm reports on the b200 arm's config)."""
     return {"workload": f"LTX-Video-2B T2V LoRA r={RANK_LORA} SFT step, 49x512x768 (2688 latent tokens/sample), "
                         f"B={B}/GPU, AdamW+clip, logit_normal sigmas", "global_batch": B * world,
-            "parallelism": f"ddp{world}",
+            "parallelism": f"{parallelism}{world}",
             "l2": "working set (3.8 GB weights + 5.5 GB activations per step) >> 126 MB L2; no flush needed",
             "random_init": True}
 
@@ -269,7 +269,10 @@ def run_b200(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()               # before CUDA work and warm-up: nothing is forked or started inside a timed region
-    be = B200ParallelBackend(backend="nccl") if world > 1 else None
+    fsdp = args.parallelism == "fsdp"
+    if fsdp and world < 2:
+        raise SystemExit("--parallelism fsdp needs --gpus >= 2 (torchrun)")
+    be = B200ParallelBackend(backend="nccl", **({"dp_shards": world} if fsdp else {})) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B = args.batch
@@ -292,7 +295,11 @@ def run_b200(args):
                 p.normal_(0, 0.01)
     model.prepare()
     if be is not None:
-        be.apply_ddp(model)
+        if fsdp:
+            be.apply_fsdp2(model, param_dtype=torch.bfloat16, reduce_dtype=torch.float32, output_dtype=None,
+                           pp_enabled=False, cpu_offload=False, device_mesh=be.get_mesh()[("dp_shard_cp",)])
+        else:
+            be.apply_ddp(model)
     # optimiser settings of the reference example (examples/training/sft/ltx_video/crush_smol_lora/train.sh:88-98)
     step = SFTTrainStep(model, flow_weighting_scheme="logit_normal", seed=42 + rank, use_cuda_graph=not args.no_graph,
                         lr=5e-5, beta1=0.9, beta2=0.99, weight_decay=1e-4, eps=1e-8, max_grad_norm=1.0,
@@ -450,13 +457,18 @@ def run_b200(args):
         "ms_per_step": ms_step, "ms_per_step_median": statistics.median(per_step), "ms_per_step_max": max(per_step),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic", "tokens_per_sec_per_gpu": value / world,
-        "config": workload_config(B, world),
+        "config": workload_config(B, world, args.parallelism),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 12,
                 "ms_per_step": ms_e2e / args.steps, "ms_per_step_median": statistics.median(per_e2e)},
         "consistency": {"value_vs_e2e_rel_diff": abs(ms_total - ms_e2e) / ms_total, "remeasured": remeasured},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-        "cuda_graph": not args.no_graph,
+        "cuda_graph": step.use_cuda_graph,
     }
+    if fsdp:
+        fs = model._fsdp
+        line["fsdp"] = {"local_param_bytes": fs.local_param_bytes(), "full_bytes_per_block": fs.full_bytes_per_block,
+                        "allgathers_per_step": (2 * (fs.nl - 2) + 1), "note": "per-block bf16 all-gather prefetched one block "
+                        "ahead on a communication stream; fp32 reduce-scatter of the flat LoRA gradient; sharded AdamW"}
     print(json.dumps(line))
     if be is not None:
         be.destroy()
@@ -471,6 +483,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--parallelism", default="ddp", choices=["ddp", "fsdp"],
+                    help="N > 1: ddp = replicas + flat gradient all-reduce (default); fsdp = FSDP-2 per-block sharding")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -204,6 +204,7 @@ class B200LTXTransformer(nn.Module):
         self._rope: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._anchor = torch.zeros((), dtype=torch.float32, device=device, requires_grad=True)
         self._saved_key = None
+        self._fsdp = None  # fsdp.FSDPState once apply_fsdp2 ran
         self._fwd_gen = 0
         self.skip_block0_dx = True
 
@@ -338,6 +339,69 @@ class B200LTXTransformer(nn.Module):
         save_file(sd, path, metadata=meta)
         return path
 
+    # ---- flat-buffer layouts -----------------------------------------------------------------------------------------
+    def _block_specs(self):
+        """(key, shape) of the tensors of ONE block's flat unit, in storage order (every size is a multiple of 8 elements,
+        so every view starts 16-byte aligned as TMA requires)."""
+        d, f = self.cfg.inner_dim, self.cfg.ffn_mult * self.cfg.inner_dim
+        return [("Wqkv", (3 * d, d)), ("bqkv", (3 * d,)), ("Wo", (d, d)), ("bo", (d,)), ("Wq2", (d, d)), ("bq2", (d,)),
+                ("Wo2", (d, d)), ("bo2", (d,)), ("W1", (f, d)), ("b1", (f,)), ("W2", (d, f)), ("b2", (d,)),
+                ("nq1", (d,)), ("nk1", (d,)), ("nq2", (d,)), ("sst", (6, d))]
+
+    def _block_params(self, blk):
+        """(key, [parameters packed into that view, in order]) for one block."""
+        a1, a2 = blk.attn1, blk.attn2
+        return [("Wqkv", [_base(a1.to_q).weight, _base(a1.to_k).weight, _base(a1.to_v).weight]),
+                ("bqkv", [_base(a1.to_q).bias, _base(a1.to_k).bias, _base(a1.to_v).bias]),
+                ("Wo", [_base(a1.to_out[0]).weight]), ("bo", [_base(a1.to_out[0]).bias]),
+                ("Wq2", [_base(a2.to_q).weight]), ("bq2", [_base(a2.to_q).bias]),
+                ("Wo2", [_base(a2.to_out[0]).weight]), ("bo2", [_base(a2.to_out[0]).bias]),
+                ("W1", [blk.ff.net[0].proj.weight]), ("b1", [blk.ff.net[0].proj.bias]),
+                ("W2", [blk.ff.net[2].weight]), ("b2", [blk.ff.net[2].bias]),
+                ("nq1", [a1.norm_q.weight]), ("nk1", [a1.norm_k.weight]), ("nq2", [a2.norm_q.weight]),
+                ("sst", [blk.scale_shift_table])]
+
+    def _root_specs(self):
+        cfg = self.cfg
+        d, nl = cfg.inner_dim, cfg.num_layers
+        return [("proj_in.w", (d, cfg.in_channels)), ("proj_in.b", (d,)), ("t1.w", (d, 256)), ("t1.b", (d,)),
+                ("t2.w", (d, d)), ("t2.b", (d,)), ("ada.w", (6 * d, d)), ("ada.b", (6 * d,)),
+                ("c1.w", (d, cfg.caption_channels)), ("c1.b", (d,)), ("c2.w", (d, d)), ("c2.b", (d,)),
+                ("sst", (2, d)), ("proj_out.w", (cfg.out_channels, d)), ("proj_out.b", (cfg.out_channels,)),
+                ("Wkv2_all", (nl, 2 * d, d)), ("bkv2_all", (nl, 2 * d)), ("nk2_all", (nl, d))]
+
+    def _root_params(self):
+        te, cp = self.time_embed, self.caption_projection
+        kw, kb, kn = [], [], []
+        for blk in self.transformer_blocks:
+            kw += [_base(blk.attn2.to_k).weight, _base(blk.attn2.to_v).weight]
+            kb += [_base(blk.attn2.to_k).bias, _base(blk.attn2.to_v).bias]
+            kn.append(blk.attn2.norm_k.weight)
+        return [("proj_in.w", [self.proj_in.weight]), ("proj_in.b", [self.proj_in.bias]),
+                ("t1.w", [te.emb.timestep_embedder.linear_1.weight]), ("t1.b", [te.emb.timestep_embedder.linear_1.bias]),
+                ("t2.w", [te.emb.timestep_embedder.linear_2.weight]), ("t2.b", [te.emb.timestep_embedder.linear_2.bias]),
+                ("ada.w", [te.linear.weight]), ("ada.b", [te.linear.bias]),
+                ("c1.w", [cp.linear_1.weight]), ("c1.b", [cp.linear_1.bias]), ("c2.w", [cp.linear_2.weight]),
+                ("c2.b", [cp.linear_2.bias]), ("sst", [self.scale_shift_table]),
+                ("proj_out.w", [self.proj_out.weight]), ("proj_out.b", [self.proj_out.bias]),
+                ("Wkv2_all", kw), ("bkv2_all", kb), ("nk2_all", kn)]
+
+    FLAT_ALIGN = 2048  # elements: every flat unit is padded so that it splits evenly over up to 8 ranks in 16-byte pieces
+
+    @classmethod
+    def _flat_numel(cls, specs):
+        n = sum((math.prod(shape) + 7) // 8 * 8 for _, shape in specs)
+        return (n + cls.FLAT_ALIGN - 1) // cls.FLAT_ALIGN * cls.FLAT_ALIGN
+
+    @staticmethod
+    def _carve(flat, specs):
+        out, o = {}, 0
+        for key, shape in specs:
+            n = math.prod(shape)
+            out[key] = flat[o:o + n].view(shape)
+            o += (n + 7) // 8 * 8
+        return out
+
     @torch.no_grad()
     def prepare(self):
         """Pack weights into the fused layouts the kernels consume and re-point the parameters into them."""
@@ -359,39 +423,38 @@ class B200LTXTransformer(nn.Module):
         # the text-side K/V projection of cross attention reads only the caption embedding, so all blocks' [Wk2;Wv2], biases
         # and norm_k weights are stacked: one batched launch per step instead of one per block
         wdt = self.proj_in.weight.dtype
-        self._Wkv2_all = torch.empty(nl, 2 * d, d, dtype=wdt, device=dev)
-        self._bkv2_all = torch.empty(nl, 2 * d, dtype=wdt, device=dev)
-        self._nk2_all = torch.empty(nl, d, dtype=wdt, device=dev)
+        # ---- base weights: ONE flat buffer per DiT block (the FSDP-2 sharding unit, ptd.py:482-499) plus one "root" flat
+        # buffer for everything outside the blocks; the module parameters become views of that storage
+        self._blk_flat = []
+        root_specs = self._root_specs()
+        self._root_flat = torch.empty(self._flat_numel(root_specs), dtype=wdt, device=dev)
+        root_views = self._carve(self._root_flat, root_specs)
+        for (key, _), (_, params) in zip(root_specs, self._root_params()):
+            v, o = root_views[key], 0
+            for prm in params:
+                n = prm.numel()
+                seg = v.reshape(-1)[o:o + n].view(prm.shape)
+                seg.copy_(prm.data)
+                prm.data = seg
+                o += n
+        self._Wkv2_all, self._bkv2_all, self._nk2_all = root_views["Wkv2_all"], root_views["bkv2_all"], root_views["nk2_all"]
+        self._root_views = root_views
+        specs = self._block_specs()
         for li, blk in enumerate(self.transformer_blocks):
             a1, a2 = blk.attn1, blk.attn2
-            e = {}
-            # fused base weights; the module parameters become views of the packed storage
-            def pack(mods, w=None, bvec=None):
-                if w is None:
-                    w = torch.cat([_base(m).weight.data for m in mods], 0).contiguous()
-                    bvec = torch.cat([_base(m).bias.data for m in mods], 0).contiguous()
-                else:
-                    w.copy_(torch.cat([_base(m).weight.data for m in mods], 0))
-                    bvec.copy_(torch.cat([_base(m).bias.data for m in mods], 0))
-                o = 0
-                for m in mods:
-                    n = _base(m).out_features
-                    _base(m).weight.data = w[o:o + n]
-                    _base(m).bias.data = bvec[o:o + n]
+            flat = torch.empty(self._flat_numel(specs), dtype=wdt, device=dev)
+            e = self._carve(flat, specs)
+            for key, params in self._block_params(blk):
+                v, o = e[key], 0
+                for prm in params:
+                    n = prm.numel()
+                    seg = v.reshape(-1)[o:o + n].view(prm.shape)
+                    seg.copy_(prm.data)
+                    prm.data = seg
                     o += n
-                return w, bvec
-            e["Wqkv"], e["bqkv"] = pack([a1.to_q, a1.to_k, a1.to_v])
-            e["Wo"], e["bo"] = _base(a1.to_out[0]).weight.data, _base(a1.to_out[0]).bias.data
-            e["Wq2"], e["bq2"] = _base(a2.to_q).weight.data, _base(a2.to_q).bias.data
-            e["Wkv2"], e["bkv2"] = pack([a2.to_k, a2.to_v], self._Wkv2_all[li], self._bkv2_all[li])
-            self._nk2_all[li].copy_(a2.norm_k.weight.data)
-            a2.norm_k.weight.data = self._nk2_all[li]
-            e["Wo2"], e["bo2"] = _base(a2.to_out[0]).weight.data, _base(a2.to_out[0]).bias.data
-            e["W1"], e["b1"] = blk.ff.net[0].proj.weight.data, blk.ff.net[0].proj.bias.data
-            e["W2"], e["b2"] = blk.ff.net[2].weight.data, blk.ff.net[2].bias.data
-            e["nq1"], e["nk1"] = a1.norm_q.weight.data, a1.norm_k.weight.data
-            e["nq2"], e["nk2"] = a2.norm_q.weight.data, a2.norm_k.weight.data
-            e["sst"] = blk.scale_shift_table.data
+            self._blk_flat.append(flat)
+            # the text-side K/V projection weights of every block live (stacked) in the root unit
+            e["Wkv2"], e["bkv2"], e["nk2"] = self._Wkv2_all[li], self._bkv2_all[li], self._nk2_all[li]
             if r:
                 base = li * per_blk
                 off = [base]
@@ -422,6 +485,35 @@ class B200LTXTransformer(nn.Module):
         self._prepared = True
         self._ws.clear()
         return self
+
+    @torch.no_grad()
+    def _rebind_flat_storage(self, block_flats, root_flat):
+        """FSDP-2: move the base-weight views of every block onto the given full-size buffers (gather slots shared by
+        several blocks) and of the root unit onto ``root_flat``, then drop the private per-block storage.  The buffers'
+        contents are only valid while the owning unit is resident (fsdp.FSDPState schedules that)."""
+        specs = self._block_specs()
+        for li, (blk, flat) in enumerate(zip(self.transformer_blocks, block_flats)):
+            views = self._carve(flat, specs)
+            for key, params in self._block_params(blk):
+                v, o = views[key], 0
+                for prm in params:
+                    n = prm.numel()
+                    prm.data = v.reshape(-1)[o:o + n].view(prm.shape)
+                    o += n
+            self._blk[li].update(views)
+        rv = self._carve(root_flat, self._root_specs())
+        for (key, _), (_, params) in zip(self._root_specs(), self._root_params()):
+            v, o = rv[key], 0
+            for prm in params:
+                n = prm.numel()
+                prm.data = v.reshape(-1)[o:o + n].view(prm.shape)
+                o += n
+        self._Wkv2_all, self._bkv2_all, self._nk2_all = rv["Wkv2_all"], rv["bkv2_all"], rv["nk2_all"]
+        for li in range(len(self._blk)):
+            self._blk[li]["Wkv2"], self._blk[li]["bkv2"], self._blk[li]["nk2"] = self._Wkv2_all[li], self._bkv2_all[li], self._nk2_all[li]
+        self._root_views = rv
+        self._blk_flat = None
+        self._root_flat = None
 
     def _attach_lora_grads(self):
         """(Re-)attach .grad views after an external ``zero_grad(set_to_none=True)``; returns True if any was missing."""
@@ -560,6 +652,9 @@ class B200LTXTransformer(nn.Module):
         x_in = hidden_states.reshape(R, Cin).to(torch.bfloat16).contiguous()
         ehs2 = ehs.reshape(RL, cfg.caption_channels).to(torch.bfloat16).contiguous()
         self.refresh_lora_operands()
+        fs = self._fsdp
+        if fs is not None:
+            fs.begin_forward()  # all-gather the root unit and the first two blocks (communication stream)
         te = self.time_embed
         # ---- timestep embedding on the B distinct timesteps (K2)
         ops.timestep_sinusoid(tvals, ws["tsin"], B)
@@ -595,6 +690,8 @@ class B200LTXTransformer(nn.Module):
         ops.qkv_norm_rope_fwd(kv2_all, 2 * d, 0, (self._nk2_all, None), 0, None, None, (ws["k2h"], ws["v2h"]), nl * B, L, H,
                               cfg.qk_norm_eps, rows_per_w=RL, w_stride=d)
         for l in range(nl):
+            if fs is not None:
+                fs.pre_block_forward(l)
             e = self._blk[l]
             sst = e["sst"]
             h_in, n1 = ws["h"][l], ws["n1"][l]
@@ -633,6 +730,8 @@ class B200LTXTransformer(nn.Module):
                      out2=ws["ffpre"][l], tag="ffn_up")
             ops.gemm(ws["f"], e["W2"], ws["h"][l + 1], M=R, N=d, K=cfg.ffn_mult * d, bias=e["b2"], epi=ops.EPI_GATE_RES,
                      res=h2, gate_table=sst[5], gate_temb=temb[:, 5 * d:], temb_stride=6 * d, rows_per_sample=S)
+            if fs is not None:
+                fs.post_block_forward(l)  # block l's weights are no longer read: its slot takes block l + 2
         ops.CONTEXT = "f.head"
         # K13: final LayerNorm + modulate (table rows 0 = shift, 1 = scale; embedded_timestep), proj_out
         t2 = self.scale_shift_table.data
@@ -716,7 +815,10 @@ class B200LTXTransformer(nn.Module):
         # (embedded has stride d, temb stride 6d: the gate of the last block is applied by a separate colscale)
         ops.colscale(ws["dh"], ws["g"], last[5], temb[:, 5 * d:], 6 * d, R, d, S)
         dh, g = ws["dh"], ws["g"]
+        fs = self._fsdp
         for l in range(nl - 1, -1, -1):
+            if fs is not None:
+                fs.pre_block_backward(l)
             e = self._blk[l]
             sst = e["sst"]
             dh2, dq2, dkv2, dyo, dqkv = ws["dy_o2"][l], ws["dy_q2"][l], ws["dy_kv2"][l], ws["dy_o"][l], ws["dy_qkv"][l]
@@ -749,13 +851,19 @@ class B200LTXTransformer(nn.Module):
                                   0b011, cos, sin, dqkv, 3 * d, 0, B, S, H, cfg.qk_norm_eps)
             du = self._lora_du(dqkv, ws["du_qkv"][l], e, "qkv", R, 3 * d, 3)
             if l == 0 and self.skip_block0_dx:
+                if fs is not None:
+                    fs.post_block_backward(l)
                 break  # nothing trainable upstream of block 0's adapters (proj_in / embeds are frozen)
             ops.gemm(dqkv, e["Wqkv"], ws["dn"], M=R, N=d, K=3 * d, b_mn=True, A2=du, B2=e["Ab_qkv"], K2=3 * rp)
             # dh0 = dh1 + norm_bwd(dn1; h_in, scale_msa=row 1) ; g = dh0 * gate_mlp of block l-1
+            if fs is not None and l > 0:
+                fs.pre_block_backward(l - 1)  # the op below reads block l-1's gate row: its all-gather must have landed
             prev = self._blk[l - 1]["sst"] if l > 0 else None
             ops.norm_modulate_bwd(ws["dn"], ws["h"][l], dh, dh, sst[1], temb[:, d:], 6 * d, R, d, S, cfg.norm_eps,
                                   gate2_tab=prev[5] if l > 0 else None, gate2_emb=temb[:, 5 * d:] if l > 0 else None,
                                   out2=g if l > 0 else None)
+            if fs is not None:
+                fs.post_block_backward(l)
         # text-side k-norm backward of all blocks in one launch (its output only feeds the adapter gradients below)
         ops.CONTEXT = "b.kv2"
         ops.qkv_norm_rope_bwd((ws["dk2h"], ws["dv2h"]), ws["kv2"].view(nl * RL, 2 * d), 2 * d, 0, (self._nk2_all, None), 0,
@@ -763,4 +871,6 @@ class B200LTXTransformer(nn.Module):
                               rows_per_w=RL, w_stride=d)
         ops.CONTEXT = "b.wgrad"
         self._lora_wgrads_all(ws, R, RL)
+        if fs is not None:
+            fs.end_backward()
         ops.CONTEXT = ""

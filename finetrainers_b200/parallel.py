@@ -180,9 +180,29 @@ class B200ParallelBackend:
         model._b200_ddp = True
         return model
 
-    def apply_fsdp2(self, *args, **kwargs):
-        raise NotImplementedError("FSDP-2 (per-block bf16 all-gather + fp32 reduce-scatter, ptd.py:466-499) is the next "
-                                  "multi-GPU row; round 1 ships DDP for the LoRA config")
+    def apply_fsdp2(self, model: torch.nn.Module, param_dtype: torch.dtype = torch.bfloat16,
+                    reduce_dtype: torch.dtype = torch.float32, output_dtype: Optional[torch.dtype] = None,
+                    pp_enabled: bool = False, cpu_offload: bool = False, device_mesh=None) -> torch.nn.Module:
+        """``PytorchDTensorParallelBackend.apply_fsdp2`` (ptd.py:100-113 -> ``apply_fsdp2`` ptd.py:466-499), same argument
+        names.  Every DiT block and the root become sharding units (``fsdp.FSDPState``); parameters are stored and
+        gathered in ``param_dtype`` (must be the model's dtype: nothing is cast), gradients are reduced in fp32."""
+        from .fsdp import FSDPState
+        if pp_enabled:
+            raise NotImplementedError("pipeline parallelism is not built (the reference's SFT loop refuses it too, trainer.py:90-93)")
+        if cpu_offload:
+            raise NotImplementedError("cpu_offload is not built (the reference passes False, trainer.py:181)")
+        if reduce_dtype not in (None, torch.float32):
+            raise NotImplementedError("gradients are reduced in fp32 (MixedPrecisionPolicy(reduce_dtype=torch.float32), trainer.py:178)")
+        wdt = next(p for n, p in model.named_parameters() if "lora_" not in n).dtype
+        if param_dtype is not None and param_dtype != wdt:
+            raise ValueError(f"param_dtype {param_dtype} != parameter dtype {wdt}: call model.to(dtype=...) first (trainer.py:133)")
+        group = device_mesh.get_group() if isinstance(device_mesh, B200Mesh) else device_mesh
+        if group is _UNIT_GROUP:
+            group = None
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("apply_fsdp2 needs an initialised process group")
+        model._fsdp = FSDPState(model, group)
+        return model
 
     def apply_context_parallel(self, *args, **kwargs):
         raise NotImplementedError("context parallelism is out of scope: LTX has no CP plan in the reference either")

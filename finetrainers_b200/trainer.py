@@ -102,8 +102,17 @@ class SFTTrainStep:
         self.generator = torch.Generator(device=dev).manual_seed(seed)
         self.scheduler_sigmas = self.scheduler.sigmas.to(dev)
         n = transformer.lora_flat.numel()
-        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.fsdp = getattr(transformer, "_fsdp", None)
+        if self.fsdp is not None:
+            # FSDP-2: optimizer state only for this rank's 1/W slice of the flat trainable buffer (fsdp.ShardedFlatOptimizer)
+            from .fsdp import ShardedFlatOptimizer
+            self.sharded_opt = ShardedFlatOptimizer(transformer.lora_flat, self.fsdp.group)
+            self.exp_avg, self.exp_avg_sq = self.sharded_opt.exp_avg, self.sharded_opt.exp_avg_sq
+            process_group = self.fsdp.group
+            use_cuda_graph = False  # the step interleaves NCCL all-gathers on a second stream: launched eagerly
+        else:
+            self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
         self.loss_acc = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -225,18 +234,31 @@ class SFTTrainStep:
     def optimizer_step(self, sync_metrics: bool = False):
         tr = self.transformer
         g = tr.lora_grad_flat
-        if self.world > 1:
-            # DDP: average the flat fp32 gradient buffer in place over NVLink (ptd.py:462-463 replicate(bucket_cap_mb=100))
-            allreduce_flat_grads(g, self.pg)
-        self.sumsq.zero_()
-        ops.sumsq(g, g.numel(), self.sumsq, self.partial)
         self.opt_step += 1
+        self.last_lr = self.lr * self._lr_factor(self.opt_step - 1)
+        if self.fsdp is not None:
+            # FSDP-2: fp32 reduce-scatter(AVG) -> global-norm clip + AdamW on the local slice -> in-place all-gather
+            def sumsq_fn(gs):
+                self.sumsq.zero_()
+                ops.sumsq(gs, gs.numel(), self.sumsq, self.partial)
+                return self.sumsq
+
+            def update_fn(p, gs, m, v, ss):
+                ops.adamw_clip(p, gs, m, v, gs.numel(), ss, self.max_grad_norm, self.last_lr, self.beta1, self.beta2,
+                               self.eps, self.wd, self.opt_step, 1.0)
+
+            self.sharded_opt.step(g, sumsq_fn, update_fn)
+        else:
+            if self.world > 1:
+                # DDP: average the flat fp32 gradient buffer in place over NVLink (ptd.py:462-463 replicate(bucket_cap_mb=100))
+                allreduce_flat_grads(g, self.pg)
+            self.sumsq.zero_()
+            ops.sumsq(g, g.numel(), self.sumsq, self.partial)
+            ops.adamw_clip(tr.lora_flat, g, self.exp_avg, self.exp_avg_sq, g.numel(), self.sumsq, self.max_grad_norm,
+                           self.last_lr, self.beta1, self.beta2, self.eps, self.wd, self.opt_step, 1.0)
         self.metrics[0:1] = self.sumsq.sqrt()
         self.metrics[1:2] = self.loss_acc
         self.metrics[2:3] = self.loss_acc
-        self.last_lr = self.lr * self._lr_factor(self.opt_step - 1)
-        ops.adamw_clip(tr.lora_flat, g, self.exp_avg, self.exp_avg_sq, g.numel(), self.sumsq, self.max_grad_norm,
-                       self.last_lr, self.beta1, self.beta2, self.eps, self.wd, self.opt_step, 1.0)
         self.loss_acc.zero_()
         self.micro = 0
         if not sync_metrics:

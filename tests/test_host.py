@@ -139,6 +139,121 @@ def test_parallel_backend_world2_gloo(tmp_path):
     assert r.stdout.count("WORKER_OK") == 2
 
 
+_FSDP_WORKER = r'''
+import os, sys, math, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["B2D_ROOT"])
+from finetrainers_b200.parallel import B200ParallelBackend
+from finetrainers_b200.fsdp import ShardedUnits, ShardedFlatOptimizer, shard_bounds
+from finetrainers_b200.model import B200LTXTransformer, LTXConfig
+be = B200ParallelBackend(backend="gloo", device_type="cpu", dp_shards=2)
+assert be.world_size == 2 and be.data_sharding_enabled and not be.data_replication_enabled and be._dp_degree == 1
+r = be.rank
+mesh = be.get_mesh()[("dp_shard_cp",)]
+assert mesh.size() == 2 and mesh.get_local_rank() == r
+
+# ---- 1. units: every rank keeps 1/W of each flat unit; gather schedule forward then backward
+flats = [torch.arange(4096, dtype=torch.float32) + 10000 * i for i in range(5)]
+su = ShardedUnits([f.clone() for f in flats], None)
+assert su.shards[3].numel() == 2048 and torch.equal(su.shards[3], flats[3][r * 2048:(r + 1) * 2048])
+su.prefetch(0); su.prefetch(1)
+for l in range(5):
+    assert torch.equal(su.wait(l), flats[l]), l
+    if l + 2 < 5:
+        su.release(l, l + 2)
+assert sorted(su.resident) == [3, 4]
+for l in range(4, -1, -1):
+    assert torch.equal(su.wait(l), flats[l]), l
+    su.release(l, l - 2)
+assert sorted(su.resident) == [0, 1] and su.gathers == 5 + 3
+try:
+    shard_bounds(10, 0, 4); raise SystemExit("uneven split accepted")
+except ValueError:
+    pass
+
+# ---- 2. sharded optimizer == AdamW + clip on the rank-averaged gradient
+torch.manual_seed(0)
+p0 = torch.randn(512)
+g_all = [torch.randn(512) * (i + 1) for i in range(2)]
+def adamw(p, g, m, v, sumsq, step=1, lr=1e-2, b1=0.9, b2=0.99, eps=1e-8, wd=1e-4, max_norm=1.0):
+    coef = min(1.0, max_norm / (math.sqrt(float(sumsq)) + 1e-6))
+    g = g * coef
+    p.mul_(1 - lr * wd)
+    m.mul_(b1).add_(g, alpha=1 - b1); v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    p.addcdiv_(m / (1 - b1 ** step), (v / (1 - b2 ** step)).sqrt() + eps, value=-lr)
+pr, mr, vr = p0.clone(), torch.zeros(512), torch.zeros(512)
+gm = (g_all[0] + g_all[1]) / 2
+adamw(pr, gm, mr, vr, (gm ** 2).sum())
+params = p0.clone()
+opt = ShardedFlatOptimizer(params, None)
+assert opt.exp_avg.numel() == 256
+grad = g_all[r].clone()
+ss = opt.step(grad, lambda gs: (gs ** 2).sum().reshape(1), lambda p, gs, m, v, s: adamw(p, gs, m, v, s))
+assert abs(float(ss) - float((gm ** 2).sum())) < 1e-3 * float(ss)
+assert torch.allclose(params, pr, atol=1e-6), (params - pr).abs().max()
+assert grad.abs().max() == 0
+
+# ---- 3. the real module: apply_fsdp2 re-binds the parameters onto gather slots; every block's weights are correct
+# while it is resident, in forward order and in backward order (incl. the previous block's gate row read by block l)
+cfg = LTXConfig(in_channels=32, out_channels=32, num_attention_heads=2, attention_head_dim=64, cross_attention_dim=128,
+                num_layers=4, caption_channels=64)
+torch.manual_seed(1)            # same weights on both ranks (apply_fsdp2 also broadcasts rank 0's)
+m = B200LTXTransformer(cfg, torch.bfloat16, "cpu")
+with torch.no_grad():
+    for p in m.parameters():
+        p.normal_(0, 0.02)
+m.add_adapter(16, 16)
+m.prepare()
+want = {k: v.clone() for k, v in m.state_dict().items()}
+total = sum(f.numel() for f in m._blk_flat) + m._root_flat.numel()
+be.apply_fsdp2(m, param_dtype=torch.bfloat16, reduce_dtype=torch.float32, output_dtype=None, pp_enabled=False,
+               cpu_offload=False, device_mesh=be.get_mesh()[("dp_shard_cp",)])
+fs = m._fsdp
+assert fs.local_param_bytes() * 2 == total * 2, (fs.local_param_bytes(), total)   # bf16: half of the elements, 2 bytes each
+assert m._blk_flat is None
+blk_keys = lambda l: [k for k in want if k.startswith(f"transformer_blocks.{l}.") and "lora_" not in k and "attn2.to_k" not in k
+                      and "attn2.to_v" not in k and "attn2.norm_k" not in k]
+sd = lambda: dict(m.named_parameters())
+fs.begin_forward()
+for k in want:
+    if not k.startswith("transformer_blocks.") or "attn2.to_k" in k or "attn2.to_v" in k or "attn2.norm_k" in k:
+        assert torch.equal(sd()[k].data, want[k]), k          # root unit resident for the whole step
+for l in range(4):
+    fs.pre_block_forward(l)
+    for k in blk_keys(l):
+        assert torch.equal(sd()[k].data, want[k]), k
+    fs.post_block_forward(l)
+for l in range(3, -1, -1):
+    fs.pre_block_backward(l)
+    for k in blk_keys(l):
+        assert torch.equal(sd()[k].data, want[k]), k
+    if l > 0:
+        fs.pre_block_backward(l - 1)
+        assert torch.equal(m._blk[l - 1]["sst"], want[f"transformer_blocks.{l - 1}.scale_shift_table"])
+    fs.post_block_backward(l)
+fs.end_backward()
+full = fs.full_state_dict()
+assert set(full) == set(want)
+for k in want:
+    assert torch.equal(full[k], want[k]), k
+be.wait_for_everyone()
+be.destroy()
+print("FSDP_WORKER_OK", r)
+'''
+
+
+def test_fsdp2_sharding_bookkeeping_world2_gloo(tmp_path):
+    """FSDP-2 (ptd.py:466-499) on the gloo backend, world 2: flat-unit sharding and the gather/release schedule, the
+    ZeRO-style sharded AdamW against plain AdamW on the averaged gradient, and ``apply_fsdp2`` on the real module."""
+    script = tmp_path / "f.py"
+    script.write_text(_FSDP_WORKER)
+    env = dict(os.environ, B2D_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)], env=env,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("FSDP_WORKER_OK") == 2
+
+
 def test_precomputed_reader_follows_reference_layout(tmp_path):
     """SURVEY §8f-2: {data_type}-{index}.pt items, rank r owns indices r*num_items + i (precomputation.py:334-341)."""
     from finetrainers_b200.data import PrecomputedReader, save_item
