@@ -393,17 +393,18 @@ def run_b200(args):
     n_k = 30
     ms_k, _ = timed(ffn_up, n_k)
     del sets
+    # every rank runs the eager step (it contains the gradient exchange); rank 0's event pairs are the ones reported
+    graph_flag = step.use_cuda_graph
+    step.use_cuda_graph = False
+    ops.KERNEL_TIMES.clear()
+    ops.TIMING = rank == 0
+    step_resident(0)
+    torch.cuda.synchronize()
+    ops.TIMING = False
+    step.use_cuda_graph = graph_flag
     in_step = None
     if rank == 0:
-        graph_flag = step.use_cuda_graph
-        step.use_cuda_graph = False
-        ops.KERNEL_TIMES.clear()
-        ops.TIMING = True
-        step_resident(0)
-        torch.cuda.synchronize()
-        ops.TIMING = False
         kt = ops.collect_kernel_times()
-        step.use_cuda_graph = graph_flag
         tot = sum(v[0] for v in kt.values())
         gemm_ms = sum(v[0] for k, v in kt.items() if k.split("/")[-1] in ("gemm", "ffn_up", "lora_u", "lora_du", "lora_dA", "lora_dB"))
         attn_ms = sum(v[0] for k, v in kt.items() if k.split("/")[-1] in ("attn_fwd", "attn_bwd"))

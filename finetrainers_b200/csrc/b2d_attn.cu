@@ -409,10 +409,14 @@ struct AttnBwdParams {
 // ================================================================================================
 // backward, pipelined: ONE CTA per SM.  The S / dP accumulators are TRIPLE-buffered in TMEM (3 x 128 columns + 128
 // columns of dV/dK or dQ accumulators = all 512), so the MMA warp runs up to three streamed tiles ahead of the two
-// consumer warpgroups, which alternate tiles.
+// consumer warpgroups, which take tiles round-robin.  Three warpgroups (one per accumulator buffer) put three consumer
+// warps on every SM sub-partition: a tile costs a warp 64 MUFU.EX2 issues (512 cycles of its sub-partition's XU) plus
+// tcgen05.ld / pack / tcgen05.st / barrier phases during which it issues none, and with only two warps per
+// sub-partition the XU idled about half the time (ncu: 40-46 % busy).
 //     MMA :  SdP(0) SdP(1) SdP(2) | dVdK(0) SdP(3) | dVdK(1) SdP(4) | ...
-//     WG0 :  [exp,dS](0)      [exp,dS](2)      [exp,dS](4) ...
-//     WG1 :       [exp,dS](1)      [exp,dS](3) ...
+//     WG0 :  [exp,dS](0)           [exp,dS](3)           ...
+//     WG1 :       [exp,dS](1)           [exp,dS](4)      ...
+//     WG2 :            [exp,dS](2)           [exp,dS](5) ...
 // P^T and dS^T never go through shared memory: each consumer thread packs its row to bf16 and writes it with tcgen05.st
 // over the first 32 columns of the S (resp. dP) buffer it has just read, and the dV / dK / dQ GEMMs take that A operand
 // from TENSOR MEMORY.  With smem-resident P^T/dS^T the dK/dV pass moved 136 KB per 64-row tile through the 128 B/clk
@@ -423,7 +427,8 @@ struct AttnBwdParams {
 constexpr int PP_TY = 64;
 constexpr int PP_STAGES = 6;                          // streamed (Y) tiles in flight
 constexpr int PP_NBUF = 3;                            // S/dP TMEM buffers
-constexpr int PP_THREADS = 320;                       // TMA warp, MMA warp, 2 x 4 consumer warps
+constexpr int PP_NWG = 3;                             // consumer warpgroups: tile `it` belongs to warpgroup it % 3 (= its buffer)
+constexpr int PP_THREADS = 64 + 128 * PP_NWG;         // TMA warp, MMA warp, 3 x 4 consumer warps
 constexpr int PP_Y_BYTES = PP_TY * HD * 2;            // 8 KB
 constexpr int PP_SMEM = 2 * TILE_BYTES + PP_STAGES * 2 * PP_Y_BYTES + PP_STAGES * 2 * PP_TY * 4 + 1024 + 256;
 
@@ -442,8 +447,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
     uint64_t* y_full = bars + 1;                   // [PP_STAGES]
     uint64_t* y_empty = y_full + PP_STAGES;        // [PP_STAGES]
     uint64_t* s_full = y_empty + PP_STAGES;        // [PP_NBUF]
-    uint64_t* ds_full = s_full + PP_NBUF;          // [2]  (per warpgroup)
-    uint64_t* all_done = ds_full + 2;
+    uint64_t* ds_full = s_full + PP_NBUF;          // [PP_NWG]  (per warpgroup)
+    uint64_t* all_done = ds_full + PP_NWG;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -468,7 +473,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             mbar_init(&y_empty[i], 1);
         }
         for (int i = 0; i < PP_NBUF; ++i) mbar_init(&s_full[i], 1);
-        for (int i = 0; i < 2; ++i) mbar_init(&ds_full[i], 128);
+        for (int i = 0; i < PP_NWG; ++i) mbar_init(&ds_full[i], 128);
         mbar_init(all_done, 1);
         fence_mbar_init();
     }
@@ -529,9 +534,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             };
             for (int it = 0; it < PP_NBUF && it < n_y; ++it) issue_sdp(it);
             for (int it = 0; it < n_y; ++it) {
-                const int bsel = it & 1;
                 const int st = it % PP_STAGES;
-                mbar_wait(&ds_full[bsel], (uint32_t)((it >> 1) & 1));  // consumer finished tile it: P^T/dS^T in TMEM
+                mbar_wait(&ds_full[it % PP_NWG], (uint32_t)((it / PP_NWG) & 1));  // consumer finished tile it: P^T/dS^T in TMEM
                 tc_fence_after();
                 const uint32_t aY1 = smem_u32(sY + st * 2 * PP_Y_BYTES), aY2 = aY1 + PP_Y_BYTES;
                 const uint32_t tP = tmem + (it % PP_NBUF) * 128, tDS = tP + 64;
@@ -554,7 +558,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             umma_commit(all_done);
         }
     } else {
-        const int wg = (warp - 2) >> 2;           // consumer warpgroup 0 / 1 handles local tiles it = wg, wg+2, ...
+        const int wg = (warp - 2) >> 2;           // consumer warpgroup wg handles local tiles it = wg, wg + 3, ...
         const int qd = warp & 3;
         const int r = qd * 32 + lane;
         const int tid128 = ((warp - 2) & 3) * 32 + lane;
@@ -570,7 +574,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             rowD = row_ok ? p.delta[bhoff * p.Sq + xrow] : 0.f;
         }
         if (!row_ok) rowA = -INFINITY;
-        for (int it = wg; it < n_y; it += 2) {
+        for (int it = wg; it < n_y; it += PP_NWG) {
             const int i = y0 + it;
             const int st = it % PP_STAGES;
             const int kb = it % PP_NBUF;
@@ -656,15 +660,16 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             tc_fence_before();
             mbar_arrive(&ds_full[wg]);
         }
-        // ---- epilogue: DKV: warpgroup 0 writes dV (out1), warpgroup 1 writes dK (out2); dQ: each takes 32 columns
+        // ---- epilogue: the 32-column pieces of the accumulators (DKV: dV lo/hi, dK lo/hi; dQ: lo/hi) go round-robin over
+        // the warpgroups
         if (n_y > 0) {
             mbar_wait(all_done, 0);
             tc_fence_after();
             const long long ro = (bhoff * rowsX + xrow) * HD;
 #pragma unroll 1
-            for (int piece = 0; piece < 2; ++piece) {
-                int which, c;
-                if (DKV) { which = wg; c = piece; } else { which = 1; c = wg; if (piece == 1) break; }
+            for (int piece = wg; piece < (DKV ? 4 : 2); piece += PP_NWG) {
+                const int which = DKV ? (piece >> 1) : 1;
+                const int c = piece & 1;
                 const uint32_t tacc = which == 0 ? tO1 : tO2;
                 const float osc = which == 0 ? 1.f : p.scale;
                 float* facc = which == 0 ? p.acc1 : p.acc2;

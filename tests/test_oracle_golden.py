@@ -1,6 +1,7 @@
 """CPU: pin the oracle restatement against golden vectors produced by the REAL reference sources
 (tests/golden/make_golden.py) and against the reference's own attention known-answer recipe
 (/root/reference/tests/models/attention_dispatch.py:41-111: randn[2,8,256,64] bf16, seed 0, vs math SDPA, atol 5e-3)."""
+import pytest
 import torch
 import torch.nn.functional as F
 
@@ -112,3 +113,38 @@ def test_clip_grad_norm_golden():
         for p, want in zip(params, g[f"{tag}_grads_out"]):
             assert torch.allclose(p.grad, want, rtol=1e-6, atol=1e-12)
     assert g["big_total_norm"] > 1.0 > g["small_total_norm"]      # one case clips, the other passes through
+
+
+def test_independent_derivation_matches_oracle():
+    """oracle/independent_constants.py re-derives the upstream-only constants (timestep sinusoid, LTX RoPE table incl.
+    padding side and pair layout, flow-match sigma table, GELU-tanh, RMSNorm) in scalar float64 without sharing code with
+    the oracle; the two must agree."""
+    import math
+    import torch
+    import torch.nn.functional as F
+    from oracle import ltx_oracle as O
+    from oracle import independent_constants as I
+    for t in (0.0, 1.0, 499.0, 999.0):
+        a = O.sinusoid_256(torch.tensor([t]))[0].double()
+        b = torch.tensor(I.sinusoid_256(t), dtype=torch.float64)
+        assert (a - b).abs().max().item() < 2e-4            # fp32 exp/cos of arguments up to 999
+    dim, Fr, H, W = 2048, 3, 4, 5
+    scale = [8 / 25, 32, 32]
+    cos, sin = O.ltx_rope_table(Fr, H, W, dim, scale)
+    assert cos.shape == (1, Fr * H * W, dim)
+    for (f, h, w) in ((0, 0, 0), (2, 3, 4), (1, 0, 3)):
+        s = (f * H + h) * W + w
+        for col in (0, 1, 2, 3, 4, 7, 8, 1000, 1001, 2046, 2047):
+            c, sn = I.rope_entry(f, h, w, col, dim, *scale)
+            assert abs(cos[0, s, col].item() - c) < 2e-3 and abs(sin[0, s, col].item() - sn) < 2e-3, (f, h, w, col)
+    # dim % 6 == 0: no padding
+    cos, sin = O.ltx_rope_table(2, 2, 2, 24, scale)
+    for col in range(24):
+        c, sn = I.rope_entry(1, 1, 0, col, 24, *scale)
+        assert abs(cos[0, (1 * 2 + 1) * 2 + 0, col].item() - c) < 2e-3   # fp32 cos of angles up to theta * pi / 2
+    assert O.flow_match_scheduler_sigmas().tolist() == pytest.approx(I.flow_match_sigmas(), abs=1e-7)
+    xs = [-3.0, -0.5, 0.0, 0.7, 2.5]
+    assert F.gelu(torch.tensor(xs), approximate="tanh").tolist() == pytest.approx([I.gelu_tanh(x) for x in xs], abs=1e-6)
+    row = [0.5, -1.0, 2.0, 0.25]
+    got = O.RMSNorm(4, 1e-5, True)(torch.tensor([row]))[0].tolist()
+    assert got == pytest.approx(I.rms_norm(row, [1.0] * 4, 1e-5), abs=1e-6)
