@@ -1,12 +1,13 @@
 // b2d_elem.cu — the HBM-bound satellites of the DiT step: fused norm+AdaLN modulate (fwd/bwd), q/k RMSNorm + RoPE +
 // head split (fwd/bwd), RoPE table, noise/pack prologue, MSE loss + dpred, sinusoid, casts, flat clip + AdamW.
-// All: 128-bit coalesced global access, fp32 math, warp-shuffle reductions; the row kernels run one warp per row.
+// All: 128-bit coalesced global access, fp32 math, warp-shuffle reductions; one row per CTA of 256 threads.
 #include "b2d_internal.h"
 #include "b2d_ptx.cuh"
 
 namespace b2d {
 
-constexpr int ROW_THREADS = 256;  // block-reduction kernels (loss, sum of squares)
+constexpr int ROW_THREADS = 256;
+constexpr int MAX_CHUNKS = 4;  // D <= 8 * 256 * 4 = 8192
 
 __device__ __forceinline__ uint4 ldg16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void stg16(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
@@ -41,185 +42,173 @@ __device__ __forceinline__ float2 block_sum2(float a, float b) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Row kernels (norm + modulate, q/k RMSNorm + RoPE + head split): ONE WARP PER ROW.
-// A row of D <= 3072 bf16 lives in registers as NCH 16-byte pieces per lane (piece c of lane l covers elements
-// [(32 c + l) * 8, +8): a warp-wide load is 512 contiguous bytes).  Reductions are five shuffles, there is no block
-// barrier and no shared memory, and the whole problem (2,688 rows at the BASELINE shape) is resident in one wave, so
-// every row's DRAM request is in flight at once - the previous CTA-per-row version spent its time in barrier round trips
-// and CTA turnover (norm+modulate forward: 11.5 us for 22 MB = 0.29 of the HBM roofline).
+// norm + modulate
 // ------------------------------------------------------------------------------------------------
-constexpr int WROW_WARPS = 8;          // warps (rows) per CTA
-constexpr int WROW_MAX_D = 3072;       // NCH <= 12
-
+// Every global operand of a row is requested BEFORE the first block reduction: a row's critical path is then one memory
+// round trip + the reductions instead of two or three dependent round trips (these kernels have ~16 KB in flight per
+// CTA and 8 CTAs per SM, so the dependent-latency chain, not bandwidth, was what bounded them).
 template <int NCH>
-struct RowRegs {
-    uint4 v[NCH];
-    __device__ __forceinline__ void load(const __nv_bfloat16* row, int D, int lane) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const int col = (c * 32 + lane) * 8;
-            v[c] = col < D ? ldg16(row + col) : make_uint4(0, 0, 0, 0);
-        }
-    }
-};
-
-// y = norm(x) * (1 + scale[b]) + shift[b]
-template <int NCH>
-__global__ void __launch_bounds__(WROW_WARPS * 32) norm_modulate_fwd_kernel(
+__global__ void __launch_bounds__(ROW_THREADS) norm_modulate_fwd_kernel(
     const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ shift_tab,
     const __nv_bfloat16* __restrict__ shift_emb, const __nv_bfloat16* __restrict__ scale_tab,
-    const __nv_bfloat16* __restrict__ scale_emb, long long emb_stride, int rows, int D, int rows_per_sample, float eps,
+    const __nv_bfloat16* __restrict__ scale_emb, long long emb_stride, int D, int rows_per_sample, float eps,
     int layer_norm) {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * WROW_WARPS + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    const int row = blockIdx.x;
     const int b = row / rows_per_sample;
-    RowRegs<NCH> xr;
-    xr.load(x + (long long)row * D, D, lane);
+    const __nv_bfloat16* xr = x + (long long)row * D;
+    uint4 xq[NCH], q_sht[NCH], q_she[NCH], q_sct[NCH], q_sce[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            xq[c] = ldg16(xr + col);
+            q_sht[c] = ldg16(shift_tab + col);
+            q_she[c] = ldg16(shift_emb + (long long)b * emb_stride + col);
+            q_sct[c] = ldg16(scale_tab + col);
+            q_sce[c] = ldg16(scale_emb + (long long)b * emb_stride + col);
+        }
+    }
+    float v[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-        float f[8];
-        unpack8(xr.v[c], f);
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            unpack8(xq[c], v[c]);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { s1 += f[e]; s2 += f[e] * f[e]; }
+            for (int e = 0; e < 8; ++e) { s1 += v[c][e]; s2 += v[c][e] * v[c][e]; }
+        }
     }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
+    float2 tot = block_sum2(s1, s2);
     float mean = 0.f, rstd;
     if (layer_norm) {
-        mean = s1 / D;
+        mean = tot.x / D;
         float var = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-            if ((c * 32 + lane) * 8 < D) {
-                float f[8];
-                unpack8(xr.v[c], f);
+            const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+            if (col < D) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { const float d = f[e] - mean; var += d * d; }
+                for (int e = 0; e < 8; ++e) { float d = v[c][e] - mean; var += d * d; }
             }
         }
-        rstd = rsqrtf(warp_sum(var) / D + eps);
+        float2 t2 = block_sum2(var, 0.f);
+        rstd = rsqrtf(t2.x / D + eps);
     } else {
-        rstd = rsqrtf(s2 / D + eps);
+        rstd = rsqrtf(tot.y / D + eps);
     }
-    const __nv_bfloat16* she = shift_emb + (long long)b * emb_stride;
-    const __nv_bfloat16* sce = scale_emb + (long long)b * emb_stride;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-        const int col = (c * 32 + lane) * 8;
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
-            float f[8], sh[8], sc[8], t[8], o[8];
-            unpack8(xr.v[c], f);
-            unpack8(ldg16(shift_tab + col), sh);
-            unpack8(ldg16(she + col), t);
+            float sh[8], sc[8], t[8];
+            unpack8(q_sht[c], sh);
+            unpack8(q_she[c], t);
 #pragma unroll
             for (int e = 0; e < 8; ++e) sh[e] += t[e];
-            unpack8(ldg16(scale_tab + col), sc);
-            unpack8(ldg16(sce + col), t);
+            unpack8(q_sct[c], sc);
+            unpack8(q_sce[c], t);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = (f[e] - mean) * rstd * (1.f + sc[e] + t[e]) + sh[e];
+            for (int e = 0; e < 8; ++e) sc[e] += t[e];
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (v[c][e] - mean) * rstd * (1.f + sc[e]) + sh[e];
             stg16(y + (long long)row * D + col, pack8(o));
         }
     }
 }
 
-// dx_out = dx_in + d norm/dx (dy * (1 + scale));  optional out2 = bf16(dx_out) * gate2[b]
 template <int NCH>
-__global__ void __launch_bounds__(WROW_WARPS * 32) norm_modulate_bwd_kernel(
+__global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dx_in,
     __nv_bfloat16* __restrict__ dx_out, const __nv_bfloat16* __restrict__ scale_tab,
     const __nv_bfloat16* __restrict__ scale_emb, const __nv_bfloat16* __restrict__ gate2_tab,
-    const __nv_bfloat16* __restrict__ gate2_emb, __nv_bfloat16* __restrict__ out2, long long emb_stride, int rows, int D,
+    const __nv_bfloat16* __restrict__ gate2_emb, __nv_bfloat16* __restrict__ out2, long long emb_stride, int D,
     int rows_per_sample, float eps, int layer_norm) {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * WROW_WARPS + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    const int row = blockIdx.x;
     const int b = row / rows_per_sample;
     const long long ro = (long long)row * D;
-    RowRegs<NCH> xr, dr, ir;
-    xr.load(x + ro, D, lane);
-    dr.load(dy + ro, D, lane);
-    if (dx_in != nullptr) ir.load(dx_in + ro, D, lane);
+    uint4 q_x[NCH], q_dy[NCH], q_sct[NCH], q_sce[NCH], q_in[NCH], q_gt[NCH], q_ge[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            q_x[c] = ldg16(x + ro + col);
+            q_dy[c] = ldg16(dy + ro + col);
+            q_sct[c] = ldg16(scale_tab + col);
+            q_sce[c] = ldg16(scale_emb + (long long)b * emb_stride + col);
+            q_in[c] = dx_in != nullptr ? ldg16(dx_in + ro + col) : make_uint4(0, 0, 0, 0);
+            if (out2 != nullptr) {
+                q_gt[c] = ldg16(gate2_tab + col);
+                q_ge[c] = ldg16(gate2_emb + (long long)b * emb_stride + col);
+            }
+        }
+    }
+    float xv[NCH][8], g[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-        float f[8];
-        unpack8(xr.v[c], f);
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            unpack8(q_x[c], xv[c]);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { s1 += f[e]; s2 += f[e] * f[e]; }
+            for (int e = 0; e < 8; ++e) { s1 += xv[c][e]; s2 += xv[c][e] * xv[c][e]; }
+        }
     }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
+    float2 tot = block_sum2(s1, s2);
     float mean = 0.f, rstd;
     if (layer_norm) {
-        mean = s1 / D;
+        mean = tot.x / D;
         float var = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-            if ((c * 32 + lane) * 8 < D) {
-                float f[8];
-                unpack8(xr.v[c], f);
+            const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+            if (col < D) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { const float d = f[e] - mean; var += d * d; }
+                for (int e = 0; e < 8; ++e) { float d = xv[c][e] - mean; var += d * d; }
             }
         }
-        rstd = rsqrtf(warp_sum(var) / D + eps);
+        rstd = rsqrtf(block_sum2(var, 0.f).x / D + eps);
     } else {
-        rstd = rsqrtf(s2 / D + eps);
+        rstd = rsqrtf(tot.y / D + eps);
     }
     // g = dy * (1 + scale);  xhat = (x - mean) * rstd;  a = sum(g), c = sum(g * xhat)
-    const __nv_bfloat16* sce = scale_emb + (long long)b * emb_stride;
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-        const int col = (c * 32 + lane) * 8;
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
-            float xv[8], d[8], sc[8], t[8];
-            unpack8(xr.v[c], xv);
-            unpack8(dr.v[c], d);
-            unpack8(ldg16(scale_tab + col), sc);
-            unpack8(ldg16(sce + col), t);
+            float sc[8], t[8], d[8];
+            unpack8(q_sct[c], sc);
+            unpack8(q_sce[c], t);
+            unpack8(q_dy[c], d);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const float g = d[e] * (1.f + sc[e] + t[e]);
-                sg += g;
-                sgx += g * ((xv[e] - mean) * rstd);
+                g[c][e] = d[e] * (1.f + sc[e] + t[e]);
+                xv[c][e] = (xv[c][e] - mean) * rstd;
+                sg += g[c][e];
+                sgx += g[c][e] * xv[c][e];
             }
         }
     }
-    sg = warp_sum(sg);
-    sgx = warp_sum(sgx);
-    const float mg = layer_norm ? sg / D : 0.f;
-    const float mgx = sgx / D;
-    const __nv_bfloat16* g2e = gate2_emb != nullptr ? gate2_emb + (long long)b * emb_stride : nullptr;
+    float2 t2 = block_sum2(sg, sgx);
+    const float mg = layer_norm ? t2.x / D : 0.f;
+    const float mgx = t2.y / D;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-        const int col = (c * 32 + lane) * 8;
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
         if (col < D) {
-            float xv[8], d[8], sc[8], t[8], o[8];
-            unpack8(xr.v[c], xv);
-            unpack8(dr.v[c], d);
-            unpack8(ldg16(scale_tab + col), sc);   // L1 hits: the same 16 bytes were read for the reduction above
-            unpack8(ldg16(sce + col), t);
-            if (dx_in != nullptr) {
-                unpack8(ir.v[c], o);
-            } else {
+            float o[8];
+            unpack8(q_in[c], o);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = 0.f;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float g = d[e] * (1.f + sc[e] + t[e]);
-                o[e] += rstd * (g - mg - ((xv[e] - mean) * rstd) * mgx);
-            }
-            const uint4 packed = pack8(o);
+            for (int e = 0; e < 8; ++e) o[e] += rstd * (g[c][e] - mg - xv[c][e] * mgx);
+            uint4 packed = pack8(o);
             stg16(dx_out + ro + col, packed);
             if (out2 != nullptr) {
                 float r[8], gt[8], ge[8];
                 unpack8(packed, r);  // the rounded value is what downstream sees
-                unpack8(ldg16(gate2_tab + col), gt);
-                unpack8(ldg16(g2e + col), ge);
+                unpack8(q_gt[c], gt);
+                unpack8(q_ge[c], ge);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) r[e] *= (gt[e] + ge[e]);
                 stg16(out2 + ro + col, pack8(r));
@@ -261,182 +250,222 @@ struct QkvSegArgs {
     long long w_stride;
 };
 
-// forward: one warp per (row, segment).  The q and k warps of a row sit next to each other in the same CTA, so the second
-// read of the row's (cos, sin) entries hits L1.
 template <int NCH>
-__global__ void __launch_bounds__(WROW_WARPS * 32) qkv_norm_rope_fwd_kernel(
+__global__ void __launch_bounds__(ROW_THREADS) qkv_norm_rope_fwd_kernel(
     const __nv_bfloat16* __restrict__ src, long long ld, long long col_off, const QkvSegArgs a,
-    const float* __restrict__ cosT, const float* __restrict__ sinT, int rows, int S, int H, float eps) {
-    const int lane = threadIdx.x & 31;
-    const int item = blockIdx.x * WROW_WARPS + (threadIdx.x >> 5);
-    if (item >= rows * a.nseg) return;
-    const int row = item / a.nseg, i = item - row * a.nseg;
+    const float* __restrict__ cosT, const float* __restrict__ sinT, int S, int H, float eps) {
     const int D = H * 64;
+    const int row = blockIdx.x;
     const int b = row / S, s = row % S;
-    // (selects instead of a.w[i]: indexing a kernel-parameter array with a run-time index forces a local-memory copy)
-    const __nv_bfloat16* w = i == 0 ? a.w[0] : (i == 1 ? a.w[1] : a.w[2]);
-    __nv_bfloat16* seg_ptr = i == 0 ? a.dst[0] : (i == 1 ? a.dst[1] : a.dst[2]);
-    if (w != nullptr && a.rows_per_w > 0) w += (long long)(row / a.rows_per_w) * a.w_stride;
-    const bool rope = (a.rope_mask >> i) & 1;
-    RowRegs<NCH> xr;
-    xr.load(src + (long long)row * ld + col_off + (long long)i * D, D, lane);
+    const __nv_bfloat16* xr = src + (long long)row * ld + col_off;
+    const long long woff = a.rows_per_w > 0 ? (long long)(row / a.rows_per_w) * a.w_stride : 0;
+    uint4 xq[3][NCH], wq[3][NCH];
     float4 c4[NCH], s4[NCH];
-    if (rope) {
-        // tables hold one (cos, sin) per rotary PAIR: [S, D/2] fp32 (the reference's repeat_interleave(2) is implicit)
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const int col = (c * 32 + lane) * 8;
-            if (col < D) {
+    for (int c = 0; c < NCH; ++c) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                if (i < a.nseg) {
+                    xq[i][c] = ldg16(xr + (long long)i * D + col);
+                    if (a.w[i] != nullptr) wq[i][c] = ldg16(a.w[i] + woff + col);
+                }
+            }
+            if (a.rope_mask) {
+                // tables hold one (cos, sin) per rotary PAIR: [S, D/2] fp32 (the reference's repeat_interleave(2) is implicit)
                 c4[c] = *reinterpret_cast<const float4*>(cosT + ((long long)s * D + col) / 2);
                 s4[c] = *reinterpret_cast<const float4*>(sinT + ((long long)s * D + col) / 2);
             }
         }
     }
-    float rstd = 1.f;
-    if (w != nullptr) {
-        float ss = 0.f;
+    float ss[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            float f[8];
-            unpack8(xr.v[c], f);
+    for (int i = 0; i < 3; ++i) {
+        if (i < a.nseg && a.w[i] != nullptr) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
-        }
-        rstd = rsqrtf(warp_sum(ss) / D + eps);
-    }
+            for (int c = 0; c < NCH; ++c) {
+                const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+                if (col < D) {
+                    float v[8];
+                    unpack8(xq[i][c], v);
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        const int col = (c * 32 + lane) * 8;
-        if (col < D) {
-            float n[8], o[8];
-            unpack8(xr.v[c], n);
-            if (w != nullptr) {
-                float wv[8];
-                unpack8(ldg16(w + col), wv);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) n[e] = n[e] * rstd * wv[e];
-            }
-            if (rope) {
-                const float cs[4] = {c4[c].x, c4[c].y, c4[c].z, c4[c].w};
-                const float sn[4] = {s4[c].x, s4[c].y, s4[c].z, s4[c].w};
-#pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                    o[e] = n[e] * cs[e >> 1] - n[e + 1] * sn[e >> 1];
-                    o[e + 1] = n[e + 1] * cs[e >> 1] + n[e] * sn[e >> 1];
+                    for (int e = 0; e < 8; ++e) ss[i] += v[e] * v[e];
                 }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = n[e];
             }
-            const int h = col >> 6, d = col & 63;
-            stg16(seg_ptr + (((long long)b * H + h) * S + s) * 64 + d, pack8(o));
+        }
+    }
+    float rstd[3] = {1.f, 1.f, 1.f};
+    if (a.w[0] != nullptr || (a.nseg > 1 && a.w[1] != nullptr)) {
+        const float2 t = block_sum2(ss[0], ss[1]);
+        rstd[0] = rsqrtf(t.x / D + eps);
+        rstd[1] = rsqrtf(t.y / D + eps);
+    }
+    if (a.nseg > 2 && a.w[2] != nullptr) rstd[2] = rsqrtf(block_sum2(ss[2], 0.f).x / D + eps);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (i < a.nseg) {
+            const bool norm = a.w[i] != nullptr;
+            const bool rope = (a.rope_mask >> i) & 1;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+                if (col < D) {
+                    float n[8];
+                    unpack8(xq[i][c], n);
+                    if (norm) {
+                        float w[8];
+                        unpack8(wq[i][c], w);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) n[e] = n[e] * rstd[i] * w[e];
+                    }
+                    float o[8];
+                    if (rope) {
+                        const float cs[4] = {c4[c].x, c4[c].y, c4[c].z, c4[c].w};
+                        const float sn[4] = {s4[c].x, s4[c].y, s4[c].z, s4[c].w};
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2) {
+                            o[e] = n[e] * cs[e >> 1] - n[e + 1] * sn[e >> 1];
+                            o[e + 1] = n[e + 1] * cs[e >> 1] + n[e] * sn[e >> 1];
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = n[e];
+                    }
+                    const int h = col >> 6, d = col & 63;
+                    stg16(a.dst[i] + (((long long)b * H + h) * S + s) * 64 + d, pack8(o));
+                }
+            }
         }
     }
 }
 
-// backward: g = rope^T(dy) * w ; xhat = x * rstd ; dx = rstd * (g - xhat * mean(g * xhat))
 template <int NCH>
-__global__ void __launch_bounds__(WROW_WARPS * 32) qkv_norm_rope_bwd_kernel(
+__global__ void __launch_bounds__(ROW_THREADS) qkv_norm_rope_bwd_kernel(
     const __nv_bfloat16* __restrict__ x, long long ld, long long col_off, const QkvSegArgs a,
     const float* __restrict__ cosT, const float* __restrict__ sinT, __nv_bfloat16* __restrict__ dx, long long ld_dx,
-    long long dx_col_off, int rows, int S, int H, float eps) {
-    const int lane = threadIdx.x & 31;
-    const int item = blockIdx.x * WROW_WARPS + (threadIdx.x >> 5);
-    if (item >= rows * a.nseg) return;
-    const int row = item / a.nseg, i = item - row * a.nseg;
+    long long dx_col_off, int S, int H, float eps) {
     const int D = H * 64;
+    const int row = blockIdx.x;
     const int b = row / S, s = row % S;
-    // (selects instead of a.w[i]: indexing a kernel-parameter array with a run-time index forces a local-memory copy)
-    const __nv_bfloat16* w = i == 0 ? a.w[0] : (i == 1 ? a.w[1] : a.w[2]);
-    __nv_bfloat16* seg_ptr = i == 0 ? a.dst[0] : (i == 1 ? a.dst[1] : a.dst[2]);
-    if (w != nullptr && a.rows_per_w > 0) w += (long long)(row / a.rows_per_w) * a.w_stride;
-    const bool rope = (a.rope_mask >> i) & 1;
-    RowRegs<NCH> xr, dr;
-    // upstream gradient in the head-split layout: 8 consecutive elements of one head row per lane
+    const __nv_bfloat16* xr = x + (long long)row * ld + col_off;
+    const long long woff = a.rows_per_w > 0 ? (long long)(row / a.rows_per_w) * a.w_stride : 0;
+    uint4 xq[3][NCH], wq[3][NCH], dq[3][NCH];
+    float4 c4[NCH], s4[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-        const int col = (c * 32 + lane) * 8;
-        dr.v[c] = col < D ? ldg16(seg_ptr + (((long long)b * H + (col >> 6)) * S + s) * 64 + (col & 63)) : make_uint4(0, 0, 0, 0);
-    }
-    if (w != nullptr) xr.load(x + (long long)row * ld + col_off + (long long)i * D, D, lane);
-    float4 c4[NCH], s4[NCH];
-    if (rope) {
+        const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+        if (col < D) {
+            const int h = col >> 6, d = col & 63;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const int col = (c * 32 + lane) * 8;
-            if (col < D) {
+            for (int i = 0; i < 3; ++i) {
+                if (i < a.nseg) {
+                    dq[i][c] = ldg16(a.dst[i] + (((long long)b * H + h) * S + s) * 64 + d);
+                    if (a.w[i] != nullptr) {
+                        xq[i][c] = ldg16(xr + (long long)i * D + col);
+                        wq[i][c] = ldg16(a.w[i] + woff + col);
+                    }
+                }
+            }
+            if (a.rope_mask) {
                 c4[c] = *reinterpret_cast<const float4*>(cosT + ((long long)s * D + col) / 2);
                 s4[c] = *reinterpret_cast<const float4*>(sinT + ((long long)s * D + col) / 2);
             }
         }
     }
-    float rstd = 1.f;
-    if (w != nullptr) {
-        float ss = 0.f;
+    float ss[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            float f[8];
-            unpack8(xr.v[c], f);
+    for (int i = 0; i < 3; ++i) {
+        if (i < a.nseg && a.w[i] != nullptr) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
+            for (int c = 0; c < NCH; ++c) {
+                const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+                if (col < D) {
+                    float v[8];
+                    unpack8(xq[i][c], v);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) ss[i] += v[e] * v[e];
+                }
+            }
         }
-        rstd = rsqrtf(warp_sum(ss) / D + eps);
     }
-    // g (kept packed as fp32 pairs would cost 2x the registers: recomputed in the second sweep instead)
-    auto grad8 = [&](int c, int col, float (&g)[8]) {
-        float dy[8];
-        unpack8(dr.v[c], dy);
-        if (rope) {
-            const float cs[4] = {c4[c].x, c4[c].y, c4[c].z, c4[c].w};
-            const float sn[4] = {s4[c].x, s4[c].y, s4[c].z, s4[c].w};
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-                g[e] = dy[e] * cs[e >> 1] + dy[e + 1] * sn[e >> 1];
-                g[e + 1] = dy[e + 1] * cs[e >> 1] - dy[e] * sn[e >> 1];
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) g[e] = dy[e];
-        }
-        if (w != nullptr) {
-            float wv[8];
-            unpack8(ldg16(w + col), wv);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) g[e] *= wv[e];
-        }
-    };
-    float mgx = 0.f;
-    if (w != nullptr) {
-        float sgx = 0.f;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const int col = (c * 32 + lane) * 8;
-            if (col < D) {
-                float g[8], xv[8];
-                grad8(c, col, g);
-                unpack8(xr.v[c], xv);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) sgx += g[e] * (xv[e] * rstd);
-            }
-        }
-        mgx = warp_sum(sgx) / D;
+    float rstd[3] = {1.f, 1.f, 1.f};
+    const bool n01 = a.w[0] != nullptr || (a.nseg > 1 && a.w[1] != nullptr);
+    const bool n2 = a.nseg > 2 && a.w[2] != nullptr;
+    if (n01) {
+        const float2 t = block_sum2(ss[0], ss[1]);
+        rstd[0] = rsqrtf(t.x / D + eps);
+        rstd[1] = rsqrtf(t.y / D + eps);
     }
+    if (n2) rstd[2] = rsqrtf(block_sum2(ss[2], 0.f).x / D + eps);
+    // g = rope^T(dy) * w ; xhat = x * rstd ; dx = rstd * (g - xhat * mean(g * xhat))
+    float g[3][NCH][8];
+    float sgx[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        const int col = (c * 32 + lane) * 8;
-        if (col < D) {
-            float g[8], o[8];
-            grad8(c, col, g);
-            if (w != nullptr) {
-                float xv[8];
-                unpack8(xr.v[c], xv);
+    for (int i = 0; i < 3; ++i) {
+        if (i < a.nseg) {
+            const bool norm = a.w[i] != nullptr;
+            const bool rope = (a.rope_mask >> i) & 1;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = rstd * (g[e] - (xv[e] * rstd) * mgx);
-            } else {
+            for (int c = 0; c < NCH; ++c) {
+                const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+                if (col < D) {
+                    float dy[8];
+                    unpack8(dq[i][c], dy);
+                    if (rope) {
+                        const float cs[4] = {c4[c].x, c4[c].y, c4[c].z, c4[c].w};
+                        const float sn[4] = {s4[c].x, s4[c].y, s4[c].z, s4[c].w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = g[e];
+                        for (int e = 0; e < 8; e += 2) {
+                            g[i][c][e] = dy[e] * cs[e >> 1] + dy[e + 1] * sn[e >> 1];
+                            g[i][c][e + 1] = dy[e + 1] * cs[e >> 1] - dy[e] * sn[e >> 1];
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) g[i][c][e] = dy[e];
+                    }
+                    if (norm) {
+                        float w[8], xv[8];
+                        unpack8(wq[i][c], w);
+                        unpack8(xq[i][c], xv);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            g[i][c][e] *= w[e];
+                            sgx[i] += g[i][c][e] * (xv[e] * rstd[i]);
+                        }
+                    }
+                }
             }
-            stg16(dx + (long long)row * ld_dx + dx_col_off + (long long)i * D + col, pack8(o));
+        }
+    }
+    float mgx[3] = {0.f, 0.f, 0.f};
+    if (n01) {
+        const float2 t = block_sum2(sgx[0], sgx[1]);
+        mgx[0] = t.x / D;
+        mgx[1] = t.y / D;
+    }
+    if (n2) mgx[2] = block_sum2(sgx[2], 0.f).x / D;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (i < a.nseg) {
+            const bool norm = a.w[i] != nullptr;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int col = (c * ROW_THREADS + threadIdx.x) * 8;
+                if (col < D) {
+                    float o[8];
+                    if (norm) {
+                        float xv[8];
+                        unpack8(xq[i][c], xv);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = rstd[i] * (g[i][c][e] - (xv[e] * rstd[i]) * mgx[i]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = g[i][c][e];
+                    }
+                    stg16(dx + (long long)row * ld_dx + dx_col_off + (long long)i * D + col, pack8(o));
+                }
+            }
         }
     }
 }
@@ -603,21 +632,18 @@ __global__ void adamw_clip_kernel(float* __restrict__ p, float* __restrict__ g, 
 using namespace b2d;
 #define STREAM reinterpret_cast<cudaStream_t>(stream)
 
-// instantiate the warp-per-row kernels for rows of up to 256 * {1, 2, 4, 8, 12} elements (registers scale with NCH)
-#define WROW_DISPATCH(D_, KERNEL, ITEMS, ...)                                                           \
-    do {                                                                                                \
-        const int nch__ = ((D_) + 255) / 256;                                                           \
-        const dim3 grid__((unsigned)(((ITEMS) + WROW_WARPS - 1) / WROW_WARPS)), blk__(WROW_WARPS * 32); \
-        if (nch__ <= 1) launch_k(KERNEL<1>, grid__, blk__, 0, STREAM, __VA_ARGS__);                     \
-        else if (nch__ == 2) launch_k(KERNEL<2>, grid__, blk__, 0, STREAM, __VA_ARGS__);                \
-        else if (nch__ <= 4) launch_k(KERNEL<4>, grid__, blk__, 0, STREAM, __VA_ARGS__);                \
-        else if (nch__ <= 8) launch_k(KERNEL<8>, grid__, blk__, 0, STREAM, __VA_ARGS__);                \
-        else launch_k(KERNEL<12>, grid__, blk__, 0, STREAM, __VA_ARGS__);                               \
+// instantiate the row kernels for 1..4 chunks of 2048 columns (registers scale with the chunk count)
+#define ROW_DISPATCH(D_, KERNEL, GRID, ...)                                             \
+    do {                                                                                \
+        const int nch__ = ((D_) + 8 * ROW_THREADS - 1) / (8 * ROW_THREADS);             \
+        if (nch__ <= 1) launch_k(KERNEL<1>, dim3(GRID), dim3(ROW_THREADS), 0, STREAM, __VA_ARGS__);       \
+        else if (nch__ == 2) launch_k(KERNEL<2>, dim3(GRID), dim3(ROW_THREADS), 0, STREAM, __VA_ARGS__);  \
+        else launch_k(KERNEL<4>, dim3(GRID), dim3(ROW_THREADS), 0, STREAM, __VA_ARGS__);                  \
     } while (0)
 
 static int check_rowop(int rows, int D, int rps) {
     if (rows <= 0 || D <= 0 || rps <= 0) return set_error(B2D_ERR_SHAPE, "rows/D/rows_per_sample must be positive");
-    if (D % 8 != 0 || D > WROW_MAX_D) return set_error(B2D_ERR_SHAPE, "D=%d must be a multiple of 8 and <= %d", D, WROW_MAX_D);
+    if (D % 8 != 0 || D > 8 * ROW_THREADS * MAX_CHUNKS) return set_error(B2D_ERR_SHAPE, "D=%d must be a multiple of 8 and <= %d", D, 8 * ROW_THREADS * MAX_CHUNKS);
     return 0;
 }
 
@@ -626,9 +652,9 @@ extern "C" int b2d_norm_modulate_fwd(const void* x, void* y, const void* shift_t
                                      int32_t D, int32_t rows_per_sample, float eps, int32_t layer_norm, void* stream) {
     B2D_BIND(x);
     if (int rc = check_rowop(rows, D, rows_per_sample)) return rc;
-    WROW_DISPATCH(D, norm_modulate_fwd_kernel, rows,
+    ROW_DISPATCH(D, norm_modulate_fwd_kernel, rows,
         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)shift_tab, (const __nv_bfloat16*)shift_emb,
-        (const __nv_bfloat16*)scale_tab, (const __nv_bfloat16*)scale_emb, emb_stride, rows, D, rows_per_sample, eps, layer_norm);
+        (const __nv_bfloat16*)scale_tab, (const __nv_bfloat16*)scale_emb, emb_stride, D, rows_per_sample, eps, layer_norm);
     B2D_CHECK_LAUNCH("norm_modulate_fwd");
     return 0;
 }
@@ -639,12 +665,10 @@ extern "C" int b2d_norm_modulate_bwd(const void* dy, const void* x, const void* 
                                      int32_t rows_per_sample, float eps, int32_t layer_norm, void* stream) {
     B2D_BIND(dy);
     if (int rc = check_rowop(rows, D, rows_per_sample)) return rc;
-    if (out2 != nullptr && (gate2_tab == nullptr || gate2_emb == nullptr))
-        return set_error(B2D_ERR_ARG, "norm_modulate_bwd: out2 needs gate2_tab and gate2_emb");
-    WROW_DISPATCH(D, norm_modulate_bwd_kernel, rows,
+    ROW_DISPATCH(D, norm_modulate_bwd_kernel, rows,
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dx_in, (__nv_bfloat16*)dx_out,
         (const __nv_bfloat16*)scale_tab, (const __nv_bfloat16*)scale_emb, (const __nv_bfloat16*)gate2_tab,
-        (const __nv_bfloat16*)gate2_emb, (__nv_bfloat16*)out2, emb_stride, rows, D, rows_per_sample, eps, layer_norm);
+        (const __nv_bfloat16*)gate2_emb, (__nv_bfloat16*)out2, emb_stride, D, rows_per_sample, eps, layer_norm);
     B2D_CHECK_LAUNCH("norm_modulate_bwd");
     return 0;
 }
@@ -667,8 +691,8 @@ static int launch_qkv_fwd(const void* src, int64_t ld, int64_t col_off, const Qk
     if ((ld % 8) || (col_off % 8)) return set_error(B2D_ERR_ALIGN, "qkv_norm_rope: ld/col_off must be multiples of 8");
     if (a.nseg < 1 || a.nseg > 3) return set_error(B2D_ERR_SHAPE, "qkv_norm_rope: 1..3 segments");
     if (a.rope_mask && (cos == nullptr || sin == nullptr)) return set_error(B2D_ERR_SHAPE, "qkv_norm_rope: rope needs tables");
-    WROW_DISPATCH(H * 64, qkv_norm_rope_fwd_kernel, (long long)B * S * a.nseg, (const __nv_bfloat16*)src, ld, col_off, a,
-                  (const float*)cos, (const float*)sin, B * S, S, H, eps);
+    ROW_DISPATCH(H * 64, qkv_norm_rope_fwd_kernel, B * S, (const __nv_bfloat16*)src, ld, col_off, a, (const float*)cos,
+                 (const float*)sin, S, H, eps);
     B2D_CHECK_LAUNCH("qkv_norm_rope_fwd");
     return 0;
 }
@@ -681,8 +705,8 @@ static int launch_qkv_bwd(const void* x, int64_t ld, int64_t col_off, const QkvS
         return set_error(B2D_ERR_ALIGN, "qkv_norm_rope_bwd: ld/col_off must be multiples of 8");
     if (a.nseg < 1 || a.nseg > 3) return set_error(B2D_ERR_SHAPE, "qkv_norm_rope_bwd: 1..3 segments");
     if (a.rope_mask && (cos == nullptr || sin == nullptr)) return set_error(B2D_ERR_SHAPE, "qkv_norm_rope_bwd: rope needs tables");
-    WROW_DISPATCH(H * 64, qkv_norm_rope_bwd_kernel, (long long)B * S * a.nseg, (const __nv_bfloat16*)x, ld, col_off, a,
-                  (const float*)cos, (const float*)sin, (__nv_bfloat16*)dx, ld_dx, dx_col_off, B * S, S, H, eps);
+    ROW_DISPATCH(H * 64, qkv_norm_rope_bwd_kernel, B * S, (const __nv_bfloat16*)x, ld, col_off, a, (const float*)cos,
+                 (const float*)sin, (__nv_bfloat16*)dx, ld_dx, dx_col_off, S, H, eps);
     B2D_CHECK_LAUNCH("qkv_norm_rope_bwd");
     return 0;
 }

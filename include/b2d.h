@@ -98,7 +98,7 @@ int b2d_gemm(const b2d_gemm_desc* d, void* stream);
  *   RMSNorm numerics finetrainers/patches/dependencies/diffusers/rms_norm.py:17-30.
  * bwd: dx_accum += d norm/dx ( dy * (1+scale) )   (adds into the residual-stream gradient; optional second output
  *   dx_scaled = dx_accum * gate2[b] for the next GEMM's A operand)
- * Row kernels run one warp per row with the row held in registers: D must be a multiple of 8 and <= 3072.
+ * Row kernels: one row per 256-thread CTA; D must be a multiple of 8 and <= 8192.
  * ------------------------------------------------------------------------------------------------------------- */
 int b2d_norm_modulate_fwd(const void* x, void* y, const void* shift_tab, const void* shift_emb, const void* scale_tab,
                           const void* scale_emb, int64_t emb_stride, int32_t rows, int32_t D, int32_t rows_per_sample,

@@ -202,7 +202,7 @@ def test_qknorm_rope_fwd_bwd(ops, which, norm, rope):
     assert rel_err(dx[:, which * D:(which + 1) * D], xf.grad.reshape(Bq * S, D)) < 1e-2
 
 
-@pytest.mark.parametrize("H,nseg", [(32, 3), (4, 3), (32, 2), (48, 3), (2, 1), (24, 2)])   # D = 64 H up to 3072 (12 pieces per lane)
+@pytest.mark.parametrize("H,nseg", [(32, 3), (4, 3), (32, 2), (96, 3), (2, 1), (24, 2)])
 def test_qkv_norm_rope_fused_segments(ops, H, nseg):
     """One launch for q|k|v (or k|v): segment i normed iff it has a weight, rotated iff its rope bit is set."""
     torch.manual_seed(3)
