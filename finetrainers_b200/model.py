@@ -757,16 +757,21 @@ class B200LTXTransformer(nn.Module):
                  c_boff=rp, ldc=n_ad * rp, alpha=self.lora_scaling, tag="lora_du")
         return du
 
-    def _lora_wgrads_all(self, ws, R, RL):
-        """dA / dB of every adapter of every block: 13 block-batched split-free GEMMs at the end of backward
-        (dB_j += dy_j^T u_j ;  dA += du^T x computed as (x^T du)^T), accumulating into the flat fp32 gradient buffer."""
+    def _lora_wgrads(self, ws, R, RL, lo=0, hi=None):
+        """dA / dB of every adapter of blocks [lo, hi): 13 block-batched split-free GEMMs (dB_j += dy_j^T u_j ;
+        dA += du^T x computed as (x^T du)^T), accumulating into the flat fp32 gradient buffer.  The whole model in one go
+        at the end of backward, or one block range at a time so that the range's slice of the flat gradient is final -
+        and its all-reduce can start - while earlier blocks are still in backward (trainer: DDP overlap)."""
         cfg = self.cfg
         d, nl, rp, pb = cfg.inner_dim, cfg.num_layers, self.rpad, self._per_blk
-        e0 = self._blk[0]
+        hi = nl if hi is None else hi
+        nr = hi - lo
+        e0 = self._blk[lo]
         # kv2 has no dX consumer, so its du is also produced here, block-batched per adapter
         for j in range(2):
-            ops.gemm(ws["dy_kv2"].view(nl * RL, 2 * d)[:, j * d:], e0["Bb_kv2"][j * d:], ws["du_kv2"].view(nl * RL, 2 * rp)[:, j * rp:],
-                     M=RL, N=rp, K=d, lda=2 * d, ldb=rp, ldc=2 * rp, b_mn=True, batch=nl, a_boff=(RL, 0), b_boff=(pb // rp, 0),
+            ops.gemm(ws["dy_kv2"].view(nl * RL, 2 * d)[lo * RL:, j * d:], e0["Bb_kv2"][j * d:],
+                     ws["du_kv2"].view(nl * RL, 2 * rp)[lo * RL:, j * rp:],
+                     M=RL, N=rp, K=d, lda=2 * d, ldb=rp, ldc=2 * rp, b_mn=True, batch=nr, a_boff=(RL, 0), b_boff=(pb // rp, 0),
                      c_boff=RL * 2 * rp, alpha=self.lora_scaling, tag="lora_du")
         groups = (("qkv", ws["dy_qkv"], ws["n1"], ws["u_qkv"], ws["du_qkv"], 3, R, R),
                   ("o", ws["dy_o"], ws["ao"], ws["u_o"], ws["du_o"], 1, R, R),
@@ -780,9 +785,9 @@ class B200LTXTransformer(nn.Module):
             # the contraction runs over the M token rows of ONE block: stacking blocks along that axis is only legal when
             # M is a whole number of 64-row k-blocks (otherwise the k-tail would read the next block's rows, not zeros)
             if M % 64 == 0:
-                spans = [(0, nl)]
+                spans = [(lo, nr)]
             else:
-                spans = [(l, 1) for l in range(nl)]
+                spans = [(l, 1) for l in range(lo, hi)]
             for (l0, nb) in spans:
                 for j in range(n_ad):
                     ops.gemm(dy2[l0 * M:, j * d:], u2[l0 * M:, j * rp:], self._blk[l0]["gB_" + g][j * d:], M=d, N=rp, K=M,
@@ -793,15 +798,27 @@ class B200LTXTransformer(nn.Module):
                          c_boff=pb, epi=ops.EPI_F32_ATOMIC_T, block_n=64, tag="lora_dA")
 
     def _backward_impl(self, dpred):
+        """The whole backward in one call (autograd path / single graph)."""
+        self._backward_head(dpred)
+        self._backward_blocks(self.cfg.num_layers - 1, 0)
+        self._backward_tail(0, self.cfg.num_layers)
+        if self._fsdp is not None:
+            self._fsdp.end_backward()
+
+    def _bwd_ctx(self):
         cfg = self.cfg
-        d, H, nl, rp = cfg.inner_dim, cfg.num_attention_heads, cfg.num_layers, self.rpad
         B, S, L, Fr, Hh, Ww, rope_scale = self._saved_key
-        R, RL = B * S, B * L
         ws = self._workspace(B, S, L)
         cos, sin = self._rope_tables(Fr, Hh, Ww, rope_scale)
-        key_bias = self._key_bias
+        return cfg, B, S, L, ws, cos, sin
+
+    def _backward_head(self, dpred):
+        """proj_out / final LayerNorm+modulate backward: leaves dh (residual-stream gradient) and g (dh x gate_mlp of the
+        last block) in the workspace."""
+        cfg, B, S, L, ws, cos, sin = self._bwd_ctx()
+        d, nl, rp = cfg.inner_dim, cfg.num_layers, self.rpad
+        R = B * S
         temb = ws["temb"]
-        scale = 1.0 / math.sqrt(cfg.attention_head_dim)
         if not rp:
             raise NotImplementedError("full-rank fine-tuning backward (base dW) is not built yet; use add_adapter()")
         if self._attach_lora_grads():
@@ -814,9 +831,19 @@ class B200LTXTransformer(nn.Module):
         ops.norm_modulate_bwd(ws["dn"], ws["h"][nl], None, ws["dh"], t2[1], ws["embedded"], d, R, d, S, 1e-6, True)
         # (embedded has stride d, temb stride 6d: the gate of the last block is applied by a separate colscale)
         ops.colscale(ws["dh"], ws["g"], last[5], temb[:, 5 * d:], 6 * d, R, d, S)
+
+    def _backward_blocks(self, l_hi, l_lo):
+        """Backward through blocks l_hi, l_hi - 1, ..., l_lo (dX through every op; per-block dy / du of the adapters are
+        stored for the batched weight-gradient GEMMs)."""
+        cfg, B, S, L, ws, cos, sin = self._bwd_ctx()
+        d, H, nl, rp = cfg.inner_dim, cfg.num_attention_heads, cfg.num_layers, self.rpad
+        R, RL = B * S, B * L
+        key_bias = self._key_bias
+        temb = ws["temb"]
+        scale = 1.0 / math.sqrt(cfg.attention_head_dim)
         dh, g = ws["dh"], ws["g"]
         fs = self._fsdp
-        for l in range(nl - 1, -1, -1):
+        for l in range(l_hi, l_lo - 1, -1):
             if fs is not None:
                 fs.pre_block_backward(l)
             e = self._blk[l]
@@ -864,13 +891,18 @@ class B200LTXTransformer(nn.Module):
                                   out2=g if l > 0 else None)
             if fs is not None:
                 fs.post_block_backward(l)
-        # text-side k-norm backward of all blocks in one launch (its output only feeds the adapter gradients below)
+        ops.CONTEXT = ""
+
+    def _backward_tail(self, lo, hi):
+        """Adapter gradients of blocks [lo, hi): the text-side k-norm backward of those blocks in one launch (its output
+        only feeds the kv2 adapter gradients), then the block-batched dA / dB GEMMs."""
+        cfg, B, S, L, ws, cos, sin = self._bwd_ctx()
+        d, H, nl = cfg.inner_dim, cfg.num_attention_heads, cfg.num_layers
+        R, RL = B * S, B * L
         ops.CONTEXT = "b.kv2"
-        ops.qkv_norm_rope_bwd((ws["dk2h"], ws["dv2h"]), ws["kv2"].view(nl * RL, 2 * d), 2 * d, 0, (self._nk2_all, None), 0,
-                              None, None, ws["dy_kv2"].view(nl * RL, 2 * d), 2 * d, 0, nl * B, L, H, cfg.qk_norm_eps,
-                              rows_per_w=RL, w_stride=d)
+        ops.qkv_norm_rope_bwd((ws["dk2h"][lo:hi], ws["dv2h"][lo:hi]), ws["kv2"].view(nl * RL, 2 * d)[lo * RL:hi * RL], 2 * d, 0,
+                              (self._nk2_all[lo:hi], None), 0, None, None, ws["dy_kv2"].view(nl * RL, 2 * d)[lo * RL:hi * RL],
+                              2 * d, 0, (hi - lo) * B, L, H, cfg.qk_norm_eps, rows_per_w=RL, w_stride=d)
         ops.CONTEXT = "b.wgrad"
-        self._lora_wgrads_all(ws, R, RL)
-        if fs is not None:
-            fs.end_backward()
+        self._lora_wgrads(ws, R, RL, lo, hi)
         ops.CONTEXT = ""

@@ -19,17 +19,20 @@ import torch
 import torch.distributed as dist
 
 
-def _avg_all_reduce(t: torch.Tensor, group=None) -> torch.Tensor:
-    """AVG all-reduce that also works on the gloo backend (CPU tests): SUM then divide."""
+def _avg_all_reduce(t: torch.Tensor, group=None, async_op: bool = False):
+    """AVG all-reduce that also works on the gloo backend (CPU tests): SUM then divide.  ``async_op`` (NCCL only) returns
+    the work handle instead of the tensor."""
     group = _group_of(group)
     if group is _UNIT_GROUP or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return t
+        return None if async_op else t
     if dist.get_backend(group) == "nccl":
-        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
+        w = dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+        if async_op:
+            return w
     else:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         t.div_(dist.get_world_size(group))
-    return t
+    return None if async_op else t   # gloo: completed synchronously, nothing to wait for
 
 
 def dist_mean(x: torch.Tensor, group=None) -> float:
@@ -64,9 +67,12 @@ def fused_step_metrics(grad_norm: torch.Tensor, loss: torch.Tensor, group=None) 
             "train/global_max_loss": max(r[1] for r in rows)}
 
 
-def allreduce_flat_grads(flat_grad: torch.Tensor, group=None, chunk_bytes: int = 0) -> torch.Tensor:
-    """Average the flat gradient buffer in place.  ``chunk_bytes`` > 0 issues several collectives (bucket_cap_mb-style)."""
+def allreduce_flat_grads(flat_grad: torch.Tensor, group=None, chunk_bytes: int = 0, async_op: bool = False):
+    """Average the flat gradient buffer in place.  ``chunk_bytes`` > 0 issues several collectives (bucket_cap_mb-style);
+    ``async_op`` issues ONE collective and returns its work handle (None when there is nothing to exchange)."""
     group = _group_of(group)
+    if async_op:
+        return _avg_all_reduce(flat_grad, group, async_op=True)
     if group is _UNIT_GROUP or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return flat_grad
     if chunk_bytes <= 0:

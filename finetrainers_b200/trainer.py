@@ -82,7 +82,7 @@ class SFTTrainStep:
                  flow_logit_std: float = 1.0, flow_mode_scale: float = 1.29, seed: int = 42,
                  process_group=None, use_cuda_graph: bool = False, lr_scheduler: str = "constant",
                  lr_warmup_steps: int = 0, train_steps: Optional[int] = None, lr_num_cycles: float = 1,
-                 lr_power: float = 1.0):
+                 lr_power: float = 1.0, ddp_chunks: int = 4):
         self.transformer = transformer
         self.spec = spec or LTXVideoModelSpecification(transformer.cfg)
         self.scheduler = FlowMatchSchedulerTable()
@@ -124,6 +124,14 @@ class SFTTrainStep:
         self.world = torch.distributed.get_world_size(process_group) if (
             torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
         self.use_cuda_graph = use_cuda_graph
+        # DDP exchange overlap: backward is cut into `ddp_chunks` block ranges; as soon as a range's adapter gradients are
+        # final (its batched dA/dB GEMMs ran) their slice of the flat buffer is all-reduced on NCCL's stream while the
+        # next range is still in backward - the role of replicate(bucket_cap_mb=100)'s bucketed reducer (ptd.py:462-463)
+        nl = transformer.cfg.num_layers
+        n_chunks = min(ddp_chunks, nl) if (self.world > 1 and self.fsdp is None) else 1
+        self._segments = [(nl * c // n_chunks, nl * (c + 1) // n_chunks) for c in range(n_chunks)][::-1]  # top blocks first
+        self._pending_ar = []
+        self._comm = torch.cuda.Stream(dev) if (n_chunks > 1 and dev.type == "cuda") else None
         self._static: Dict[tuple, Dict[str, torch.Tensor]] = {}
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self._eager_runs: Dict[tuple, int] = {}
@@ -149,8 +157,8 @@ class SFTTrainStep:
             self._static[key] = st
         return key, st
 
-    def _body(self, key, st):
-        """prologue + forward + loss + backward on the static buffers (capturable: no host sync, no data-dependent
+    def _body_front(self, key, st):
+        """prologue + forward + loss + head backward on the static buffers (capturable: no host sync, no data-dependent
         Python control flow)."""
         B, C, Fr, Hh, Ww, L, Cc = key
         tr = self.transformer
@@ -164,8 +172,51 @@ class SFTTrainStep:
         pred = tr._forward_impl(st["x_t"], st["ehs"], tvals, key_bias, Fr, Hh, Ww, rope_scale)
         ops.loss_mse(pred, st["target"], weights, 1.0 / self.grad_accum, self.loss_buf, st["dpred"], self.partial, B,
                      pred.shape[1] * pred.shape[2])
-        tr._backward_impl(st["dpred"])
+        tr._backward_head(st["dpred"])
         self.loss_acc += self.loss_buf
+
+    def _body_segment(self, key, st, seg: int, segments):
+        """Segment `seg` of the step: (front part for seg 0) + backward through its block range + that range's adapter
+        gradients."""
+        tr = self.transformer
+        lo, hi = segments[seg]
+        if seg == 0:
+            self._body_front(key, st)
+        tr._backward_blocks(hi - 1, lo)
+        tr._backward_tail(lo, hi)
+        if seg == len(segments) - 1 and tr._fsdp is not None:
+            tr._fsdp.end_backward()
+
+    def _run_segment(self, key, st, seg: int, segments):
+        """Eager, or one CUDA-graph replay per (shape, segmentation, segment)."""
+        if not self.use_cuda_graph:
+            self._body_segment(key, st, seg, segments)
+            return
+        gkey = (key, len(segments), seg)
+        g = self._graphs.get(gkey)
+        if g is None:
+            n = self._eager_runs.get(gkey, 0)
+            if n < 2:  # warm-up eagerly (lazy one-time work: rope tables, func attributes, workspace allocation)
+                self._body_segment(key, st, seg, segments)
+                self._eager_runs[gkey] = n + 1
+                return
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body_segment(key, st, seg, segments)
+            self._graphs[gkey] = g
+        g.replay()
+
+    def _allreduce_range_async(self, lo: int, hi: int):
+        """Average blocks [lo, hi)'s slice of the flat gradient buffer across ranks on NCCL's stream, ordered after the
+        work issued so far on the compute stream."""
+        tr = self.transformer
+        sl = tr.lora_grad_flat[lo * tr._per_blk:hi * tr._per_blk]
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ev)
+            self._pending_ar.append(allreduce_flat_grads(sl, self.pg, async_op=True))
 
     # -- forward + loss + backward of one micro-batch (trainer.py:436-483) ---------------------------------------
     @torch.no_grad()
@@ -207,25 +258,15 @@ class SFTTrainStep:
             st["sig_ff"].copy_(torch.clamp(ff, max=self.spec.min_first_frame_sigma))
         else:
             st["sig_ff"].copy_(st["sig"])  # first latent frame uses the same sigma: identical to the plain branch
-        # ---- the step body: eager, or one CUDA-graph replay
-        if not self.use_cuda_graph:
-            self._body(key, st)
-        else:
-            g = self._graphs.get(key)
-            if g is None:
-                n = self._eager_runs.get(key, 0)
-                if n < 2:  # warm-up eagerly (lazy one-time work: rope tables, func attributes, workspace allocation)
-                    self._body(key, st)
-                    self._eager_runs[key] = n + 1
-                else:
-                    torch.cuda.synchronize()
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        self._body(key, st)
-                    self._graphs[key] = g
-                    g.replay()
-            else:
-                g.replay()
+        # ---- the step body: eager, or CUDA-graph replays.  On the micro-step that completes an accumulation window under
+        # DDP the backward runs in block-range segments with each range's gradient all-reduce issued behind it.
+        last_micro = (self.micro + 1) % self.grad_accum == 0
+        nl = self.transformer.cfg.num_layers
+        segments = self._segments if (len(self._segments) > 1 and last_micro) else [(0, nl)]
+        for seg in range(len(segments)):
+            self._run_segment(key, st, seg, segments)
+            if len(segments) > 1:
+                self._allreduce_range_async(*segments[seg])
         self.micro += 1
         return self.loss_buf
 
@@ -249,7 +290,12 @@ class SFTTrainStep:
 
             self.sharded_opt.step(g, sumsq_fn, update_fn)
         else:
-            if self.world > 1:
+            if self._pending_ar:
+                for w in self._pending_ar:   # the chunked exchange was issued behind each backward segment
+                    if w is not None:
+                        w.wait()
+                self._pending_ar.clear()
+            elif self.world > 1:
                 # DDP: average the flat fp32 gradient buffer in place over NVLink (ptd.py:462-463 replicate(bucket_cap_mb=100))
                 allreduce_flat_grads(g, self.pg)
             self.sumsq.zero_()

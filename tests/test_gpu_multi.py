@@ -28,10 +28,12 @@ if mode == "fsdp":
     assert bm._fsdp is not None and bm._blk_flat is None
 else:
     be.apply_ddp(bm, be.get_mesh())
-st = SFTTrainStep(bm, flow_weighting_scheme="none", lr=1e-3, seed=5)
+st = SFTTrainStep(bm, flow_weighting_scheme="none", lr=1e-3, seed=5, use_cuda_graph=(mode == "ddp_graph"),
+                  ddp_chunks=(1 if mode == "ddp_serial" else 2))
+assert len(st._segments) == (2 if mode in ("ddp", "ddp_graph") else 1)
 st.spec.first_frame_conditioning_p = 0.0
 losses = []
-for i in range(4):
+for i in range(6 if mode == "ddp_graph" else 4):    # graph mode: 2 eager warm-ups, capture, replays
     batch = O.make_synthetic_batch(om.cfg, 2, 2, 4, 9, text_len=24, seed=900 + 10 * i + r, text_scale=1.0)   # rank-specific data
     dev = f"cuda:{be.local_rank}"
     cond = {"encoder_hidden_states": batch["encoder_hidden_states"].to(dev), "encoder_attention_mask": batch["encoder_attention_mask"].to(dev)}
@@ -59,7 +61,7 @@ def test_fsdp2_matches_ddp_over_nccl(tmp_path):
     script.write_text(_WORKER)
     out = str(tmp_path / "res")
     env = dict(os.environ, B2D_ROOT=ROOT, B2D_OUT=out, MASTER_ADDR="127.0.0.1", NCCL_DEBUG="WARN")
-    for mode, port in (("ddp", "29551"), ("fsdp", "29552")):
+    for mode, port in (("ddp", "29551"), ("fsdp", "29552"), ("ddp_serial", "29553"), ("ddp_graph", "29554")):
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                             "--master-addr", "127.0.0.1", "--master-port", port, str(script), mode], env=env,
                            capture_output=True, text=True, timeout=280)
@@ -70,5 +72,12 @@ def test_fsdp2_matches_ddp_over_nccl(tmp_path):
         assert abs(la - lb) / abs(la) < 1e-4 and abs(ma - mb) / abs(ma) < 1e-4 and abs(ga - gb) / abs(ga) < 1e-3
     # same reduction, same AdamW: only the order of the fp32 gradient sum differs (all-reduce vs reduce-scatter)
     assert (a["lora"] - b["lora"]).abs().max().item() < 2e-5
+    # the overlapped exchange (two block ranges, all-reduced behind their backward segments) is the serial exchange,
+    # and the segment graphs replay what the eager segments compute
+    c, d = torch.load(out + ".ddp_serial"), torch.load(out + ".ddp_graph")
+    assert (a["lora"] - c["lora"]).abs().max().item() < 1e-6
+    for (la, ma, ga), (lc, mc, gc), (ld, md, gd) in zip(a["losses"], c["losses"], d["losses"]):
+        assert abs(la - lc) / abs(la) < 1e-6 and abs(ga - gc) / abs(ga) < 1e-5
+        assert abs(la - ld) / abs(la) < 1e-5 and abs(ga - gd) / abs(ga) < 1e-4
     # 4 blocks: forward gathers 0..3, backward re-gathers 1, 0 (3 and 2 stay resident); the next step finds 0 and 1 resident
     assert b["gathers"] == 4 + 2 + 3 * (2 + 2)
