@@ -178,41 +178,34 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
         float m_run = -INFINITY, l_run = 0.f;
         const float* kb = p.key_bias ? p.key_bias + (long long)b * p.Sk : nullptr;
-        // Software pipeline across tiles.  tcgen05.ld moves 16 B/clk per sub-partition, so a warp's 64-column row costs as
-        // many cycles on the TMEM read port (512) as its 64 exponentials cost on the XU; issued back to back per tile the
-        // two phases serialise inside a warp (ncu: both units ~56 % busy).  Here the first 32 columns of tile j+1 (the
-        // other S buffer, normally long complete) are requested before the second half of tile j is exponentiated, and
-        // the second half of tile j is requested before its first half is: every tcgen05.ld overlaps MUFU work of the same warp.
-        uint32_t va[32], vb[32];
-        bool have_a = false;   // va holds (or is receiving) S[:, 0:32] of the current tile
         for (int j = 0; j < n_kv; ++j) {
             const uint32_t tS = tmem + (j & 1) * 64 + lane_off;
-            if (!have_a) {
-                mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
-                tc_fence_after();
-                tmem_ld32(tS, va);
-            }
-            tmem_ld_wait();            // va complete
-            tmem_ld32(tS + 32, vb);    // in flight while va is consumed
-            have_a = false;
+            mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
             const int kv0 = j * FDB_KV;
             const bool fast = (kb == nullptr) && (kv0 + FDB_KV <= p.Sk);
             bool done = false;
             if (fast && j > 0) {
                 // Optimistic pass against the running maximum.  No per-element max: every term is >= 0, so a term above 2^8
                 // forces the tile's row sum above 2^8 as well - the sum (needed anyway) is the overflow detector, at worst
-                // sending a harmless tile through the exact path below.  scale/offset FMAs and the row-sum adds run as
-                // packed fp32 pairs (FFMA2 / FADD2).
+                // sending a harmless tile through the exact two-pass path.  scale/offset FMAs and the row-sum adds run as
+                // packed fp32 pairs (FFMA2 / FADD2).  Both 32-column halves are requested before the first is consumed.
                 uint64_t l01 = f2_pack(0.f, 0.f), l23 = l01;
                 const uint64_t nm2 = f2_pack(-m_run, -m_run), scale2 = f2_pack(p.scale_log2, p.scale_log2);
-                uint32_t wa[16], wb[16];   // packed bf16 P, kept until the overflow check has passed
-                {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(tS, v0);
+                tmem_ld32(tS + 32, v1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
                     float pv[32];
 #pragma unroll
                     for (int e = 0; e < 32; e += 4) {
+                        const float a0 = __uint_as_float(c ? v1[e] : v0[e]), a1 = __uint_as_float(c ? v1[e + 1] : v0[e + 1]);
+                        const float a2 = __uint_as_float(c ? v1[e + 2] : v0[e + 2]), a3 = __uint_as_float(c ? v1[e + 3] : v0[e + 3]);
                         float x0, x1, x2, x3;
-                        f2_unpack(f2_fma(f2_pack(__uint_as_float(va[e]), __uint_as_float(va[e + 1])), scale2, nm2), x0, x1);
-                        f2_unpack(f2_fma(f2_pack(__uint_as_float(va[e + 2]), __uint_as_float(va[e + 3])), scale2, nm2), x2, x3);
+                        f2_unpack(f2_fma(f2_pack(a0, a1), scale2, nm2), x0, x1);
+                        f2_unpack(f2_fma(f2_pack(a2, a3), scale2, nm2), x2, x3);
                         pv[e] = fast_exp2(x0);
                         pv[e + 1] = fast_exp2(x1);
                         pv[e + 2] = fast_exp2(x2);
@@ -220,36 +213,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
                         l01 = f2_add(l01, f2_pack(pv[e], pv[e + 1]));
                         l23 = f2_add(l23, f2_pack(pv[e + 2], pv[e + 3]));
                     }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) wa[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
-                }
-                tmem_ld_wait();            // vb complete
-                const bool pre = (j + 1 < n_kv) && (kb == nullptr) && (kv0 + 2 * FDB_KV <= p.Sk);
-                if (pre) {
-                    // next tile's first half: its S MMA was issued before this tile's softmax started
-                    mbar_wait(&s_full[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
-                    tc_fence_after();
-                }
-                if (pre) {  // va is recycled: should the optimistic pass fail, this tile's first half is re-read (P is stored later)
-                    tmem_ld32(tmem + ((j + 1) & 1) * 64 + lane_off, va);
-                    have_a = true;
-                }
-                {
-                    float pv[32];
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4) {
-                        float x0, x1, x2, x3;
-                        f2_unpack(f2_fma(f2_pack(__uint_as_float(vb[e]), __uint_as_float(vb[e + 1])), scale2, nm2), x0, x1);
-                        f2_unpack(f2_fma(f2_pack(__uint_as_float(vb[e + 2]), __uint_as_float(vb[e + 3])), scale2, nm2), x2, x3);
-                        pv[e] = fast_exp2(x0);
-                        pv[e + 1] = fast_exp2(x1);
-                        pv[e + 2] = fast_exp2(x2);
-                        pv[e + 3] = fast_exp2(x3);
-                        l01 = f2_add(l01, f2_pack(pv[e], pv[e + 1]));
-                        l23 = f2_add(l23, f2_pack(pv[e + 2], pv[e + 3]));
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) wb[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+                    tmem_store_bf16x32(tS + c * 16, pv);
                 }
                 float l0, l1, l2, l3;
                 f2_unpack(l01, l0, l1);
@@ -257,17 +221,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
                 const float l_tile = (l0 + l1) + (l2 + l3);
                 if (!__any_sync(0xffffffffu, !(l_tile <= 256.0f))) {  // negated compare: NaN / inf also take the exact path
                     l_run += l_tile;
-                    tmem_st16(tS, wa);
-                    tmem_st16(tS + 16, wb);
                     done = true;
                 } else {
-                    // exact redo: second half from registers, first half re-read from the (still unmodified) S buffer
-                    uint32_t vr[32];
-                    tmem_ld32(tS, vr);
-                    tmem_ld_wait();  // also drains the prefetch into va
+                    // the optimistic P already overwrote S[:, 0:32): this buffer's scores are gone, so the exact path must
+                    // not re-read them.  Recover: keep what was loaded in registers (v0 / v1 still hold the raw scores).
                     float mx = -INFINITY;
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(vr[e]), __uint_as_float(vb[e])));
+                    for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
                     mx *= p.scale_log2;
                     float m_use = m_run;
                     const bool need = (mx - m_run) > 8.0f;
@@ -290,34 +250,33 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
                     }
                     m_run = m_use;
                     float l0e = 0.f;
-                    {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
                         float pv[32];
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
-                            pv[e] = fast_exp2(fmaf(__uint_as_float(vr[e]), p.scale_log2, -m_use));
-                            l0e += pv[e];
+                            const float pe = fast_exp2(fmaf(__uint_as_float(c ? v1[e] : v0[e]), p.scale_log2, -m_use));
+                            pv[e] = pe;
+                            l0e += pe;
                         }
-                        tmem_store_bf16x32(tS, pv);
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            pv[e] = fast_exp2(fmaf(__uint_as_float(vb[e]), p.scale_log2, -m_use));
-                            l0e += pv[e];
-                        }
-                        tmem_store_bf16x32(tS + 16, pv);
+                        tmem_store_bf16x32(tS + c * 16, pv);
                     }
                     l_run += l0e;
                     done = true;
                 }
             }
             if (!done) {
-                // exact two-pass path: first tile, key bias, ragged last tile (no prefetch: va / vb are this tile's halves)
+                // exact two-pass path: first tile, key bias, ragged last tile
+                uint32_t v0[32], v1[32];
+                tmem_ld32(tS, v0);
+                tmem_ld32(tS + 32, v1);
                 tmem_ld_wait();
                 float x[64];
                 float mx = -INFINITY;
 #pragma unroll
                 for (int e = 0; e < 64; ++e) {
                     const int col = kv0 + e;
-                    float xe = __uint_as_float(e < 32 ? va[e] : vb[e - 32]) * p.scale_log2;
+                    float xe = __uint_as_float(e < 32 ? v0[e] : v1[e - 32]) * p.scale_log2;
                     if (kb) xe += kb[min(col, p.Sk - 1)] * LOG2E;
                     xe = col < p.Sk ? xe : -INFINITY;
                     x[e] = xe;
