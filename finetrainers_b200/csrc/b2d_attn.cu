@@ -407,9 +407,12 @@ struct AttnBwdParams {
 };
 
 // ================================================================================================
-// backward, pipelined: ONE CTA per SM.  The S / dP accumulators are TRIPLE-buffered in TMEM (3 x 128 columns + 128
-// columns of dV/dK or dQ accumulators = all 512), so the MMA warp runs up to three streamed tiles ahead of the two
-// consumer warpgroups, which take tiles round-robin.  Three warpgroups (one per accumulator buffer) put three consumer
+// backward, pipelined: ONE CTA per SM.  The S / dP accumulators live in FOUR TMEM buffers of 2 x 48 columns (4 x 96 + 128
+// columns of dV/dK or dQ accumulators = all 512) for THREE consumer warpgroups, which take 48-row tiles round-robin.
+// One more buffer than warpgroups is what decouples them from the tensor pipe: the S/dP of a warpgroup's NEXT tile
+// (it + 3, buffer (it + 3) % 4) is issued when tile it - 1 is released, i.e. while the warpgroup is still working on
+// tile it.  With one buffer per warpgroup (3 x 128 columns, 64-row tiles) a clock64 trace showed every warpgroup
+// waiting ~1000 of its ~2500 cycles per tile for "its" S/dP to be recomputed (profiles/r2_attention_phase_trace_*).  Three warpgroups (one per accumulator buffer) put three consumer
 // warps on every SM sub-partition: a tile costs a warp 64 MUFU.EX2 issues (512 cycles of its sub-partition's XU) plus
 // tcgen05.ld / pack / tcgen05.st / barrier phases during which it issues none, and with only two warps per
 // sub-partition the XU idled about half the time (ncu: 40-46 % busy).
@@ -424,13 +427,77 @@ struct AttnBwdParams {
 // work; the TS form leaves the 64 KB of K/V/Q/dO operand reads.  The tensor pipe executes in issue order, so SdP(it+3),
 // issued after dVdK(it), overwrites the columns dVdK(it) reads only after it has consumed them.
 // ================================================================================================
-constexpr int PP_TY = 64;
-constexpr int PP_STAGES = 6;                          // streamed (Y) tiles in flight
-constexpr int PP_NBUF = 3;                            // S/dP TMEM buffers
-constexpr int PP_NWG = 3;                             // consumer warpgroups: tile `it` belongs to warpgroup it % 3 (= its buffer)
+constexpr int PP_TY = 48;                             // rows of a streamed tile
+constexpr int PP_STAGES = 8;                          // streamed (Y) tiles in flight
+constexpr int PP_NBUF = 4;                            // S/dP TMEM buffers (2 x 48 columns each): tile `it` uses buffer it % 4
+constexpr int PP_NWG = 3;                             // consumer warpgroups: tile `it` belongs to warpgroup it % 3
 constexpr int PP_THREADS = 64 + 128 * PP_NWG;         // TMA warp, MMA warp, 3 x 4 consumer warps
-constexpr int PP_Y_BYTES = PP_TY * HD * 2;            // 8 KB
+constexpr int PP_Y_BYTES = PP_TY * HD * 2;            // 6 KB (a whole number of 1024-byte swizzle atoms)
+constexpr int PP_BUF_COLS = 2 * PP_TY;                // S | dP of one buffer
+static_assert(PP_NBUF * PP_BUF_COLS + 128 <= 512, "S/dP buffers + the two 64-column accumulators must fit tensor memory");
+static_assert(PP_TY % 16 == 0 && PP_TY <= 64, "tile width: whole k-steps, at most two tcgen05.ld chunks");
 constexpr int PP_SMEM = 2 * TILE_BYTES + PP_STAGES * 2 * PP_Y_BYTES + PP_STAGES * 2 * PP_TY * 4 + 1024 + 256;
+
+// One tcgen05.ld chunk of NC (32 or 16) score columns starting at column c0 of this thread's row: P = exp2(S*scale + a),
+// dS = P * (dP - d) with the per-column terms a / d read from shared memory (or absent: no_col), written back as bf16
+// pairs over columns [c0/2, c0/2 + NC/2) of the same S / dP buffers.
+template <bool DKV, int NC>
+__device__ __forceinline__ void pp_consume(uint32_t tS, uint32_t tDP, int c0, uint32_t aCA, uint32_t aCD, bool no_col,
+                                           bool add_row, float rowA, float rowD, float scale_log2) {
+    uint32_t sv[NC], dv[NC];
+    tmem_ld_n<NC>(tS + c0, sv);
+    tmem_ld_n<NC>(tDP + c0, dv);
+    float pe[NC], ds[NC];
+    const uint64_t scale2 = f2_pack(scale_log2, scale_log2);
+    if (no_col) {
+        const uint64_t rowA2 = f2_pack(rowA, rowA), rowD2 = f2_pack(rowD, rowD);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < NC; e += 2) {
+            float x0, x1;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), scale2, rowA2), x0, x1);
+            pe[e] = fast_exp2(x0);
+            pe[e + 1] = fast_exp2(x1);
+            const uint64_t t2 = f2_sub(f2_pack(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), rowD2);
+            f2_unpack(f2_mul(f2_pack(pe[e], pe[e + 1]), t2), ds[e], ds[e + 1]);
+        }
+    } else {
+        float ca[NC], cd[NC];
+#pragma unroll
+        for (int u = 0; u < NC / 4; ++u) {
+            const float4 t = lds128f(aCA + (c0 + u * 4) * 4);
+            ca[u * 4] = t.x; ca[u * 4 + 1] = t.y; ca[u * 4 + 2] = t.z; ca[u * 4 + 3] = t.w;
+            if (DKV) {
+                const float4 d4 = lds128f(aCD + (c0 + u * 4) * 4);
+                cd[u * 4] = d4.x; cd[u * 4 + 1] = d4.y; cd[u * 4 + 2] = d4.z; cd[u * 4 + 3] = d4.w;
+            }
+        }
+        if (add_row) {
+#pragma unroll
+            for (int e = 0; e < NC; ++e) ca[e] += rowA;
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < NC; e += 2) {
+            float x0, x1;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), scale2, f2_pack(ca[e], ca[e + 1])), x0, x1);
+            pe[e] = fast_exp2(x0);
+            pe[e + 1] = fast_exp2(x1);
+            const uint64_t sub2 = DKV ? f2_pack(cd[e], cd[e + 1]) : f2_pack(rowD, rowD);
+            const uint64_t t2 = f2_sub(f2_pack(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), sub2);
+            f2_unpack(f2_mul(f2_pack(pe[e], pe[e + 1]), t2), ds[e], ds[e + 1]);
+        }
+    }
+    uint32_t w[NC / 2];
+    if (DKV) {
+#pragma unroll
+        for (int i = 0; i < NC / 2; ++i) w[i] = pack_bf16x2(pe[2 * i], pe[2 * i + 1]);
+        if constexpr (NC == 32) tmem_st16(tS + c0 / 2, w); else tmem_st8(tS + c0 / 2, w);
+    }
+#pragma unroll
+    for (int i = 0; i < NC / 2; ++i) w[i] = pack_bf16x2(ds[2 * i], ds[2 * i + 1]);
+    if constexpr (NC == 32) tmem_st16(tDP + c0 / 2, w); else tmem_st8(tDP + c0 / 2, w);
+}
 
 template <bool DKV>
 __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid_constant__ AttnBwdParams p) {
@@ -485,7 +552,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // S[k] at 128*k (P^T[k] = bf16 pairs over its first 32 columns), dP[k] at 128*k + 64 (dS^T[k] likewise), k = 0..2;
+    // S[k] at 96*k (P^T[k] = bf16 pairs over its first 24 columns), dP[k] at 96*k + 48 (dS^T[k] likewise), k = 0..3;
     // out1 at 384, out2 at 448
     const uint32_t tO1 = tmem + 384, tO2 = tmem + 448;
 
@@ -522,7 +589,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
                 mbar_wait(&y_full[st], (uint32_t)((it / PP_STAGES) & 1));
                 tc_fence_after();
                 const uint32_t aY1 = smem_u32(sY + st * 2 * PP_Y_BYTES), aY2 = aY1 + PP_Y_BYTES;
-                const uint32_t tS = tmem + (it % PP_NBUF) * 128, tDP = tS + 64;
+                const uint32_t tS = tmem + (it % PP_NBUF) * PP_BUF_COLS, tDP = tS + TY;
                 const uint32_t ly1 = sdesc_lo_kmajor(aY1), ly2 = sdesc_lo_kmajor(aY2);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -538,7 +605,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
                 mbar_wait(&ds_full[it % PP_NWG], (uint32_t)((it / PP_NWG) & 1));  // consumer finished tile it: P^T/dS^T in TMEM
                 tc_fence_after();
                 const uint32_t aY1 = smem_u32(sY + st * 2 * PP_Y_BYTES), aY2 = aY1 + PP_Y_BYTES;
-                const uint32_t tP = tmem + (it % PP_NBUF) * 128, tDS = tP + 64;
+                const uint32_t tP = tmem + (it % PP_NBUF) * PP_BUF_COLS, tDS = tP + TY;
                 if (DKV) {
                     const uint32_t ly = sdesc_lo_mnmajor(aY2);
 #pragma unroll
@@ -552,7 +619,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
                         umma_f16_ts_lo(tO2, tDS + k * TMEM_A_KSTEP, ly + k * SDESC_KSTEP_MNMAJOR, idesc_o, (it > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&y_empty[st]);
-                // refill the buffer only now: S/dP(it+3) overwrite the columns the two GEMMs above read (issue order)
+                // refill THIS buffer only now: S/dP(it + 4) overwrite the columns the two GEMMs above read (issue order)
                 if (it + PP_NBUF < n_y) issue_sdp(it + PP_NBUF);
             }
             umma_commit(all_done);
@@ -578,7 +645,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             const int i = y0 + it;
             const int st = it % PP_STAGES;
             const int kb = it % PP_NBUF;
-            const uint32_t tS = tmem + kb * 128 + lane_off, tDP = tS + 64;
+            const uint32_t tS = tmem + kb * PP_BUF_COLS + lane_off, tDP = tS + TY;
             float* cA = sColA + st * TY;
             float* cD = sColD + st * TY;
             const bool full_tile = (i + 1) * TY <= rowsY;
@@ -604,58 +671,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             const uint32_t aCA = smem_u32(cA), aCD = smem_u32(cD);
             // the per-row term is only non-trivial with a key bias or a ragged X tile (DKV), resp. it carries -lse (dQ pass)
             const bool add_row = !DKV || p.key_bias != nullptr || !row_ok;
-#pragma unroll 1
-            for (int c = 0; c < TY / 32; ++c) {
-                uint32_t sv[32], dv[32];
-                tmem_ld32(tS + c * 32, sv);
-                tmem_ld32(tDP + c * 32, dv);
-                float pe[32], ds[32];
-                const uint64_t scale2 = f2_pack(p.scale_log2, p.scale_log2);
-                if (no_col) {
-                    const uint64_t rowA2 = f2_pack(rowA, rowA), rowD2 = f2_pack(rowD, rowD);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        float x0, x1;
-                        f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), scale2, rowA2), x0, x1);
-                        pe[e] = fast_exp2(x0);
-                        pe[e + 1] = fast_exp2(x1);
-                        const uint64_t t2 = f2_sub(f2_pack(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), rowD2);
-                        f2_unpack(f2_mul(f2_pack(pe[e], pe[e + 1]), t2), ds[e], ds[e + 1]);
-                    }
-                } else {
-                    float ca[32], cd[32];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const float4 t = lds128f(aCA + (c * 32 + u * 4) * 4);
-                        ca[u * 4] = t.x; ca[u * 4 + 1] = t.y; ca[u * 4 + 2] = t.z; ca[u * 4 + 3] = t.w;
-                        if (DKV) {
-                            const float4 d4 = lds128f(aCD + (c * 32 + u * 4) * 4);
-                            cd[u * 4] = d4.x; cd[u * 4 + 1] = d4.y; cd[u * 4 + 2] = d4.z; cd[u * 4 + 3] = d4.w;
-                        }
-                    }
-                    if (add_row) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) ca[e] += rowA;
-                    }
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        float x0, x1;
-                        f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), scale2,
-                                         f2_pack(ca[e], ca[e + 1])), x0, x1);
-                        pe[e] = fast_exp2(x0);
-                        pe[e + 1] = fast_exp2(x1);
-                        const uint64_t sub2 = DKV ? f2_pack(cd[e], cd[e + 1]) : f2_pack(rowD, rowD);
-                        const uint64_t t2 = f2_sub(f2_pack(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), sub2);
-                        f2_unpack(f2_mul(f2_pack(pe[e], pe[e + 1]), t2), ds[e], ds[e + 1]);
-                    }
-                }
-                // chunk c's bf16 pairs land in columns [16 c, 16 c + 16) of the S (resp. dP) buffer: columns this thread
-                // has already read (chunk 0) or that hold chunk-0 values consumed above (chunk 1)
-                if (DKV) tmem_store_bf16x32(tS + c * 16, pe);
-                tmem_store_bf16x32(tDP + c * 16, ds);
-            }
+            // 48 columns = one 32-column and one 16-column tcgen05.ld chunk; chunk c's bf16 pairs land in columns
+            // [c0 / 2, c0 / 2 + NC / 2) of the S (resp. dP) buffer: columns this thread has already read
+            pp_consume<DKV, 32>(tS, tDP, 0, aCA, aCD, no_col, add_row, rowA, rowD, p.scale_log2);
+            if (TY > 32) pp_consume<DKV, (TY > 32 ? TY - 32 : 16)>(tS, tDP, 32, aCA, aCD, no_col, add_row, rowA, rowD, p.scale_log2);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&ds_full[wg]);
