@@ -303,7 +303,7 @@ def run_b200(args):
     # optimiser settings of the reference example (examples/training/sft/ltx_video/crush_smol_lora/train.sh:88-98)
     step = SFTTrainStep(model, flow_weighting_scheme="logit_normal", seed=42 + rank, use_cuda_graph=not args.no_graph,
                         lr=5e-5, beta1=0.9, beta2=0.99, weight_decay=1e-4, eps=1e-8, max_grad_norm=1.0,
-                        lr_scheduler="constant_with_warmup", lr_warmup_steps=1000)
+                        lr_scheduler="constant_with_warmup", lr_warmup_steps=1000, ddp_chunks=args.ddp_chunks)
 
     # ---- synthetic data: a small pool of pinned host batches, plus one device-resident copy
     g = torch.Generator().manual_seed(1234 + rank)
@@ -484,6 +484,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--ddp-chunks", type=int, default=4, help="N > 1, ddp: block-range chunks of the overlapped gradient exchange (1 = one serial all-reduce)")
     ap.add_argument("--parallelism", default="ddp", choices=["ddp", "fsdp"],
                     help="N > 1: ddp = replicas + flat gradient all-reduce (default); fsdp = FSDP-2 per-block sharding")
     args = ap.parse_args()
