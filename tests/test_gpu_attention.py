@@ -25,7 +25,10 @@ def test_reference_attention_kat_through_provider_hook():
         out = attention_dispatch(q, k, v)
     assert out.shape == ref.shape
     assert (out.float() - ref.float()).abs().max().item() < 5e-3
-    # backward recipe: output.mean().backward(), compare grads at atol 1e-3
+    # backward recipe: output.mean().backward(), compare grads at atol 1e-3.  NB: this is the reference's own recipe and it is
+    # nearly vacuous (the gradients of a mean over 262k outputs are O(4e-6), far below the tolerance); it is kept because it
+    # is the check the reference holds.  The backward kernels are actually held to 2 % of each gradient's scale against
+    # fp32 math attention in test_attention_fwd_bwd_shapes below.
     grads = []
     for fn in (lambda a, b, c: _math_sdpa(a, b, c), lambda a, b, c: attention_dispatch(a, b, c)):
         qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
