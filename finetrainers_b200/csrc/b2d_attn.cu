@@ -66,6 +66,9 @@ struct AttnFwdParams {
 // leaves only K and V tiles and Q on that port.  (The tensor pipe executes in issue order: S(j+2), issued after PV(j),
 // overwrites the columns PV(j) reads only after PV(j) has consumed them.)
 // ================================================================================================
+#ifndef FDB_POLY_MASK
+#define FDB_POLY_MASK 0x8888u   // 4 of every 16 pairs: 25 % of the exponentials leave MUFU (2/16 .. 4/16 measured equal, 6/16 slower)
+#endif
 constexpr int FDB_KV = 64;                                  // key rows per tile
 constexpr int FDB_STAGES = 4;
 constexpr int FDB_KV_BYTES = FDB_KV * HD * 2;               // 8 KB (K or V tile)
@@ -185,33 +188,42 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
             const int kv0 = j * FDB_KV;
             const bool fast = (kb == nullptr) && (kv0 + FDB_KV <= p.Sk);
             bool done = false;
-            if (fast && j > 0) {
+            if (fast) {
                 // Optimistic pass against the running maximum.  No per-element max: every term is >= 0, so a term above 2^8
                 // forces the tile's row sum above 2^8 as well - the sum (needed anyway) is the overflow detector, at worst
                 // sending a harmless tile through the exact two-pass path.  scale/offset FMAs and the row-sum adds run as
                 // packed fp32 pairs (FFMA2 / FADD2).  Both 32-column halves are requested before the first is consumed.
+                // FDB_POLY_MASK picks, per 32-column half, the pairs whose exponentials are evaluated on the FMA pipe
+                // (exp2_poly_x2) instead of MUFU: with two CTAs per SM the 16 ex2/clk/SM of the special-function unit is the
+                // binding resource of this loop (64-key tile = 512 MUFU cycles per warp, two warps per sub-partition).
                 uint64_t l01 = f2_pack(0.f, 0.f), l23 = l01;
-                const uint64_t nm2 = f2_pack(-m_run, -m_run), scale2 = f2_pack(p.scale_log2, p.scale_log2);
                 uint32_t v0[32], v1[32];
                 tmem_ld32(tS, v0);
                 tmem_ld32(tS + 32, v1);
                 tmem_ld_wait();
+                if (j == 0) {  // first tile: the running maximum is this tile's row maximum
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
+                    m_run = mx * p.scale_log2;
+                }
+                const uint64_t nm2 = f2_pack(-m_run, -m_run), scale2 = f2_pack(p.scale_log2, p.scale_log2);
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     float pv[32];
 #pragma unroll
-                    for (int e = 0; e < 32; e += 4) {
-                        const float a0 = __uint_as_float(c ? v1[e] : v0[e]), a1 = __uint_as_float(c ? v1[e + 1] : v0[e + 1]);
-                        const float a2 = __uint_as_float(c ? v1[e + 2] : v0[e + 2]), a3 = __uint_as_float(c ? v1[e + 3] : v0[e + 3]);
-                        float x0, x1, x2, x3;
+                    for (int i = 0; i < 16; ++i) {
+                        const float a0 = __uint_as_float(c ? v1[2 * i] : v0[2 * i]), a1 = __uint_as_float(c ? v1[2 * i + 1] : v0[2 * i + 1]);
+                        float x0, x1;
                         f2_unpack(f2_fma(f2_pack(a0, a1), scale2, nm2), x0, x1);
-                        f2_unpack(f2_fma(f2_pack(a2, a3), scale2, nm2), x2, x3);
-                        pv[e] = fast_exp2(x0);
-                        pv[e + 1] = fast_exp2(x1);
-                        pv[e + 2] = fast_exp2(x2);
-                        pv[e + 3] = fast_exp2(x3);
-                        l01 = f2_add(l01, f2_pack(pv[e], pv[e + 1]));
-                        l23 = f2_add(l23, f2_pack(pv[e + 2], pv[e + 3]));
+                        if ((FDB_POLY_MASK >> i) & 1) {
+                            exp2_poly_x2(f2_pack(fmaxf(x0, -126.f), fmaxf(x1, -126.f)), pv[2 * i], pv[2 * i + 1]);
+                        } else {
+                            pv[2 * i] = fast_exp2(x0);
+                            pv[2 * i + 1] = fast_exp2(x1);
+                        }
+                        if (i & 1) l23 = f2_add(l23, f2_pack(pv[2 * i], pv[2 * i + 1]));
+                        else l01 = f2_add(l01, f2_pack(pv[2 * i], pv[2 * i + 1]));
                     }
                     tmem_store_bf16x32(tS + c * 16, pv);
                 }
@@ -266,7 +278,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
                 }
             }
             if (!done) {
-                // exact two-pass path: first tile, key bias, ragged last tile
+                // exact two-pass path: key bias, ragged last tile
                 uint32_t v0[32], v1[32];
                 tmem_ld32(tS, v0);
                 tmem_ld32(tS + 32, v1);

@@ -226,6 +226,27 @@ __device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+__device__ __forceinline__ uint64_t f2_add_rm(uint64_t a, uint64_t b) {  // round toward -inf
+    uint64_t d;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// 2^x for a pair of lanes WITHOUT the special-function unit (x in [-126, ~100]; the caller clamps): Cody-Waite split
+// x = n + f by a round-down add of 1.5 * 2^23 (n lands in the low mantissa bits), a cubic for 2^f on [0, 1) (max relative
+// error 8.8e-5, far below the bf16 rounding P gets next) evaluated as three packed FMAs, and n added into the exponent field
+// with an integer shift-add.  ~4 issue slots per element on the FMA / integer pipes against 1 slot + 1/16 clk/SM of MUFU:
+// the softmax loop sends a fraction of its exponentials this way because MUFU (16 ex2/clk/SM) is its binding unit.
+__device__ __forceinline__ void exp2_poly_x2(uint64_t x2, float& y0, float& y1) {
+    const uint64_t magic = 0x4B4000004B400000ull;  // {12582912.f, 12582912.f}
+    const uint64_t xr = f2_add_rm(x2, magic);
+    const uint64_t fr = f2_sub(x2, f2_sub(xr, magic));
+    const uint64_t c3 = 0x3D9DF09D3D9DF09Dull, c2 = 0x3E6906A43E6906A4ull, c1 = 0x3F31F5193F31F519ull, c0 = 0x3F8000003F800000ull;
+    const uint64_t r = f2_fma(f2_fma(f2_fma(c3, fr, c2), fr, c1), fr, c0);
+    const uint32_t n0 = (uint32_t)xr, n1 = (uint32_t)(xr >> 32), r0 = (uint32_t)r, r1 = (uint32_t)(r >> 32);
+    y0 = __uint_as_float(r0 + (n0 << 23));
+    y1 = __uint_as_float(r1 + (n1 << 23));
+}
 __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
     uint64_t d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));

@@ -8,6 +8,10 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from finetrainers_b200 import lib  # noqa: E402
+
+if "--lib" in sys.argv:  # time another build of the library (tools/micro/poly_exp_variants.py)
+    lib.LIB_PATH = sys.argv[sys.argv.index("--lib") + 1]
 from finetrainers_b200 import ops  # noqa: E402
 
 dev = "cuda"
@@ -50,6 +54,29 @@ print("err fwd %.2e dq %.2e dk %.2e dv %.2e" % (rel(ao.view(B, S, H, 64)[:, :, :
 tf, tb = t(fwd), t(bwd)
 gf = 4.0 * S * S * 64 * H * B / 1e6
 print("b200  fwd %7.1f us (%6.1f TFLOP/s)   bwd %7.1f us (%6.1f TFLOP/s at 2.5x fwd flops)" % (tf, gf / tf, tb, 2.5 * gf / tb), flush=True)
+if "--long" in sys.argv:
+    # ~1 s of back-to-back launches of each direction with NVML clock / power samples: shows whether a number is
+    # taken at the power cap (SM clock well below its maximum) rather than at full clocks
+    import threading
+    import time
+    import pynvml
+    pynvml.nvmlInit()
+    hnd = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+    for name, fn, n in (("fwd", fwd, 10000), ("bwd", bwd, 4000)):
+        samples, stop = [], threading.Event()
+
+        def sampler():
+            while not stop.is_set():
+                samples.append((pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(hnd) / 1e3))
+                time.sleep(0.02)
+        th = threading.Thread(target=sampler)
+        th.start()
+        us = t(fn, n)
+        stop.set()
+        th.join()
+        half = samples[len(samples) // 2:]
+        print("long %s: %7.1f us over %d launches; SM clock median %d MHz, power median %.0f W (second half of the loop)" % (
+            name, us, n, sorted(c for c, _ in half)[len(half) // 2], sorted(w for _, w in half)[len(half) // 2]), flush=True)
 if "--no-sdpa" not in sys.argv:
     from torch.nn.attention import SDPBackend, sdpa_kernel
     for name, be in (("cudnn", SDPBackend.CUDNN_ATTENTION), ("flash", SDPBackend.FLASH_ATTENTION)):

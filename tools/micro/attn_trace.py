@@ -26,7 +26,7 @@ for _ in range(3):
     ops.attn_fwd(q, k, v, None, ao, lse, B, H, S, S, 0.125)
     ops.attn_bwd(q, k, v, None, ao, dout, lse, delta, dq, dk, dv, B, H, S, S, 0.125)
 torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 8192)()
+buf = (ctypes.c_longlong * 16384)()
 assert lib.load().b2d_trace_read(buf) == 0
 t = list(buf)
 
@@ -53,3 +53,24 @@ show("forward softmax warp (CTA (3,5)): per 64-key tile", 0, 42, ["wait_S", "ld"
 for nm, base in (("backward dQ pass, warpgroup 0", 4096), ("backward dQ pass, warpgroup 1", 4096 + 1024),
                  ("backward dK/dV pass, warpgroup 0", 4096 + 2048), ("backward dK/dV pass, warpgroup 1", 4096 + 2048 + 1024)):
     show(nm + ": per 64-row tile of that warpgroup", base, 16, ["pre", "wait_S", "compute", "st+arrive"])
+
+
+def show_mma(name, base, n=56):
+    rows = [t[base + i * 4: base + i * 4 + 4] for i in range(n) if t[base + i * 4] != 0]
+    if len(rows) < 12:
+        return
+    mid = rows[4:-4]
+    w_ds = sum(r[1] - r[0] for r in mid) / len(mid)
+    issue_out = sum(r[2] - r[1] for r in mid) / len(mid)
+    w_y = sum(r[3] - r[2] for r in mid) / len(mid)
+    per = (mid[-1][0] - mid[0][0]) / (len(mid) - 1)
+    print(f"{name}: MMA-issuing thread per tile: wait_dS={w_ds:6.1f} accumulate+commit={issue_out:6.1f} wait_Y={w_y:6.1f} "
+          f"issue_SdP+loop={per - w_ds - issue_out - w_y:6.1f}  period={per:6.1f} clk/tile")
+
+
+show_mma("backward dQ pass", 8192)
+show_mma("backward dK/dV pass", 8192 + 2048)
+for nm, o in (("dQ", 16000), ("dK/dV", 16008)):
+    c0, g0, c1, g1 = t[o:o + 4]
+    if g1 > g0:
+        print(f"backward {nm} pass, CTA (3,5): {c1 - c0} clk in {(g1 - g0) / 1e3:.1f} us -> SM clock {(c1 - c0) / (g1 - g0) * 1e3:.0f} MHz")
