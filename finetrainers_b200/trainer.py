@@ -2,8 +2,8 @@
 (``/root/reference/finetrainers/trainer/sft_trainer/trainer.py:397-529``) rebuilt around the B200 engine.
 
 Kept from the reference: sigma sampling (``utils/diffusion.py:38-63,84-114``), loss weighting (``:117-130``), the
-loss definition (``trainer.py:474-481``), clip-then-AdamW ordering (``:488-503``), gradient accumulation, and the
-per-step metrics (``global_avg_loss``, ``global_max_loss``, ``grad_norm``; ``:507-520``).
+loss definition (``trainer.py:474-481``), clip-then-AdamW ordering (``:488-503``), gradient accumulation (including the
+reference's clip after EVERY micro-step, ``train_step`` -> ``clip_accumulated``), and the per-step metrics (``global_avg_loss``, ``global_max_loss``, ``grad_norm``; ``:507-520``).
 
 Changed for B200: loss + dloss/dpred is one kernel; LoRA gradients land in one flat fp32 buffer that is all-reduced in
 place (DDP) and consumed by one fused clip+AdamW kernel; the three scalar reductions are one 3-float all-reduce; the
@@ -311,9 +311,30 @@ class SFTTrainStep:
             return None
         return fused_step_metrics(self.metrics[0], self.metrics[1], self.pg)
 
+    @torch.no_grad()
+    def clip_accumulated(self):
+        """The reference clips after EVERY micro-step's backward (``trainer.py:486-493`` sits outside the
+        ``step % gradient_accumulation_steps`` test), so inside an accumulation window the PARTIALLY accumulated gradient is
+        rescaled to ``max_grad_norm`` before the next micro-step adds to it.  Under DDP / FSDP-2 the reference's gradient
+        is already averaged over ranks at that point; the buffer holds (previous, identical on every rank) + (this rank's
+        micro-gradient), so averaging the whole buffer gives exactly that."""
+        g = self.transformer.lora_grad_flat
+        if self._pending_ar:
+            for w in self._pending_ar:
+                if w is not None:
+                    w.wait()
+            self._pending_ar.clear()
+        elif self.world > 1:
+            allreduce_flat_grads(g, self.pg)
+        if self.max_grad_norm is not None and self.max_grad_norm > 0:
+            self.sumsq.zero_()
+            ops.sumsq(g, g.numel(), self.sumsq, self.partial)
+            g.mul_(torch.clamp(self.max_grad_norm / (self.sumsq.sqrt() + 1e-6), max=1.0))
+
     def train_step(self, condition_model_conditions, latent_model_conditions, sigmas=None, noise=None,
                    sync_metrics=False):
         self.micro_step(condition_model_conditions, latent_model_conditions, sigmas, noise)
         if self.micro % self.grad_accum == 0:
             return self.optimizer_step(sync_metrics)
+        self.clip_accumulated()
         return None

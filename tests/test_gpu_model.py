@@ -240,6 +240,59 @@ def test_cuda_graph_step_matches_eager_and_grad_accumulation():
     assert torch.allclose(bm.lora_grad_flat, gs[0] + gs[1], rtol=1e-4, atol=1e-9)
 
 
+def test_grad_accumulation_clips_after_every_micro_step_like_the_reference():
+    """trainer.py:486-493 calls clip_grad_norm_ after every micro-step's backward, accumulation boundary or not: with a
+    max_grad_norm far below the gradient norm the partially accumulated gradient is rescaled before the second micro-step
+    adds to it.  The b200 train_step must leave the same flat gradient direction / length as torch autograd on the oracle
+    run the reference's way, and the same AdamW update."""
+    from finetrainers_b200.trainer import SFTTrainStep
+    O, om, bm = build_pair(SMALL, 64, seed=4)
+    max_norm = 1e-3
+    st = SFTTrainStep(bm, flow_weighting_scheme="none", lr=1e-3, max_grad_norm=max_norm, gradient_accumulation_steps=2, seed=3)
+    st.spec.first_frame_conditioning_p = 0.0
+    params = [p for n, p in om.named_parameters() if "lora_" in n]
+    opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.99), weight_decay=1e-4, eps=1e-8)
+    p0 = {n: p.detach().clone() for n, p in om.named_parameters() if "lora_" in n}
+    opt.zero_grad(set_to_none=True)
+    norms = []
+    for i in range(2):
+        batch = O.make_synthetic_batch(om.cfg, 1, 2, 4, 8, text_len=16, seed=400 + i, text_scale=1.0)
+        cond = {"encoder_hidden_states": batch["encoder_hidden_states"].cuda(), "encoder_attention_mask": batch["encoder_attention_mask"].cuda()}
+        lat = {"latents": batch["latents"].cuda(), "latents_mean": batch["latents_mean"].cuda(), "latents_std": batch["latents_std"].cuda()}
+        if i == 0:
+            st.train_step(cond, lat, sigmas=batch["sigmas"].view(-1).cuda(), noise=batch["noise"].cuda())
+            torch.cuda.synchronize()
+            # after the first micro-step the accumulated gradient has been clipped to max_norm
+            assert abs(bm.lora_grad_flat.norm().item() - max_norm) / max_norm < 1e-3
+        else:
+            st.micro_step(cond, lat, sigmas=batch["sigmas"].view(-1).cuda(), noise=batch["noise"].cuda())
+        fb = {k: (v.float() if v.is_floating_point() else v) for k, v in batch.items()}
+        pred, target, sig = O.spec_forward(om, fb["latents"], fb["latents_mean"], fb["latents_std"], fb["encoder_hidden_states"],
+                                           fb["encoder_attention_mask"], fb["sigmas"], noise=fb["noise"])
+        (O.sft_loss(pred, target, sig) / 2).backward()          # trainer.py:479-480: loss / gradient_accumulation_steps
+        norms.append(float(O.clip_grad_norm_(params, max_norm)))  # every micro-step
+    torch.cuda.synchronize()
+    # second micro-step: (clipped first gradient, norm 1e-3) + (raw second gradient): dominated by the second, as in the oracle
+    g_b = bm.lora_grad_flat.norm().item()
+    assert abs(g_b - norms[1]) / norms[1] < 3e-2, (g_b, norms)
+    assert norms[0] > 10 * max_norm      # the first clip really was active
+    opt.step()
+    st.optimizer_step()
+    torch.cuda.synchronize()
+    og = dict(om.named_parameters())
+    checked = 0
+    for n, p in bm.named_parameters():
+        if "lora_" in n:
+            db = (p.detach().float().cpu() - p0[n]).flatten()
+            do = (og[n].detach() - p0[n]).flatten()
+            if do.norm() == 0:
+                continue
+            cos = torch.dot(db, do) / (db.norm() * do.norm())
+            assert cos > 0.95 and abs(db.norm() / do.norm() - 1) < 0.05, (n, cos.item(), (db.norm() / do.norm()).item())
+            checked += 1
+    assert checked >= 30
+
+
 def test_three_step_trajectory_first_frame_conditioning_and_lr_schedule():
     """Three optimizer steps of the b200 step against the oracle run the way the reference trainer runs them: first-frame
     conditioning branch taken (base_specification.py:298-310), sigma-dependent loss weights, clip + AdamW under a
