@@ -83,6 +83,7 @@ __device__ __forceinline__ void tmem_store_bf16x32(uint32_t taddr, const float (
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __grid_constant__ AttnFwdParams p) {
+    griddep_launch_dependents();
     extern __shared__ uint8_t smem_fdb[];  // no static smem: the dynamic window starts 1024-aligned
     uint8_t* smem = smem_fdb;
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;  // S[b] at 64*b (P[b] = bf16 pairs over its first 32 columns), O at 128
+    griddep_wait();  // everything above touched only shared / tensor memory and kernel parameters
     const uint32_t tO = tmem + 128;
 
     if (warp == 0) {
@@ -379,6 +381,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_db_kernel(const __gri
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                                   const float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ nlse2,
                                   int B, int H, int Sq) {
+    griddep_launch_dependents();
+    griddep_wait();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * Sq * H * 8;
     const bool ok = t < total;
@@ -513,6 +517,7 @@ __device__ __forceinline__ void pp_consume(uint32_t tS, uint32_t tDP, int c0, ui
 
 template <bool DKV>
 __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid_constant__ AttnBwdParams p) {
+    griddep_launch_dependents();
     constexpr int TY = PP_TY;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -564,6 +569,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    griddep_wait();  // everything above touched only shared / tensor memory and kernel parameters
     // S[k] at 96*k (P^T[k] = bf16 pairs over its first 24 columns), dP[k] at 96*k + 48 (dS^T[k] likewise), k = 0..3;
     // out1 at 384, out2 at 448
     const uint32_t tO1 = tmem + 384, tO2 = tmem + 448;
@@ -783,6 +789,7 @@ __device__ __forceinline__ void x_load_bias(float* sBias, const float* key_bias,
 }
 
 __global__ void __launch_bounds__(X_THREADS, 1) attn_xfwd_kernel(const __grid_constant__ AttnXParams p) {
+    griddep_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;
@@ -805,7 +812,10 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xfwd_kernel(const __grid_co
     const int n_qt = (p.Sq + TILE - 1) / TILE;
     const int t0 = blockIdx.x * p.tiles_per_cta;
     const int n = min(p.tiles_per_cta, n_qt - t0);
-    if (n <= 0) return;
+    if (n <= 0) {
+        griddep_wait();  // even an idle CTA completes only after the prerequisite grids (completion is transitive)
+        return;
+    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmQ);
@@ -831,6 +841,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xfwd_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;  // S[g] at 128*g, O[g] at 256 + 64*g
+    griddep_wait();  // everything above touched only shared / tensor memory and kernel parameters
 
     if (warp == 0) {
         if (elect_one()) {
@@ -988,6 +999,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xfwd_kernel(const __grid_co
 }
 
 __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_constant__ AttnXParams p) {
+    griddep_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;
@@ -1012,7 +1024,10 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_co
     const int n_qt = (p.Sq + TILE - 1) / TILE;
     const int t0 = blockIdx.x * p.tiles_per_cta;
     const int n = min(p.tiles_per_cta, n_qt - t0);
-    if (n <= 0) return;
+    if (n <= 0) {
+        griddep_wait();  // even an idle CTA completes only after the prerequisite grids (completion is transitive)
+        return;
+    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmQ);
@@ -1041,6 +1056,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    griddep_wait();  // everything above touched only shared / tensor memory and kernel parameters
     // S at 0 (128 key columns), dP at 128, dV at 256, dK at 320, dQ[j] at 384 + 64*j
     const uint32_t tDV = tmem + 256, tDK = tmem + 320;
 
@@ -1319,6 +1335,8 @@ __global__ void __launch_bounds__(X_THREADS, 1) attn_xbwd_kernel(const __grid_co
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+    griddep_launch_dependents();
+    griddep_wait();
     long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         float4 v = *reinterpret_cast<const float4*>(src + i);

@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_fwd_kernel(
     const __nv_bfloat16* __restrict__ shift_emb, const __nv_bfloat16* __restrict__ scale_tab,
     const __nv_bfloat16* __restrict__ scale_emb, long long emb_stride, int D, int rows_per_sample, float eps,
     int layer_norm) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int row = blockIdx.x;
     const int b = row / rows_per_sample;
     const __nv_bfloat16* xr = x + (long long)row * D;
@@ -125,6 +127,8 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
     const __nv_bfloat16* __restrict__ scale_emb, const __nv_bfloat16* __restrict__ gate2_tab,
     const __nv_bfloat16* __restrict__ gate2_emb, __nv_bfloat16* __restrict__ out2, long long emb_stride, int D,
     int rows_per_sample, float eps, int layer_norm) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int row = blockIdx.x;
     const int b = row / rows_per_sample;
     const long long ro = (long long)row * D;
@@ -220,6 +224,8 @@ __global__ void __launch_bounds__(ROW_THREADS) norm_modulate_bwd_kernel(
 __global__ void colscale_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                 const __nv_bfloat16* __restrict__ tab, const __nv_bfloat16* __restrict__ emb,
                                 long long emb_stride, long long total8, int D, int rows_per_sample) {
+    griddep_launch_dependents();
+    griddep_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total8) return;
     long long e0 = i * 8;
@@ -254,6 +260,8 @@ template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS) qkv_norm_rope_fwd_kernel(
     const __nv_bfloat16* __restrict__ src, long long ld, long long col_off, const QkvSegArgs a,
     const float* __restrict__ cosT, const float* __restrict__ sinT, int S, int H, float eps) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int D = H * 64;
     const int row = blockIdx.x;
     const int b = row / S, s = row % S;
@@ -345,6 +353,8 @@ __global__ void __launch_bounds__(ROW_THREADS) qkv_norm_rope_bwd_kernel(
     const __nv_bfloat16* __restrict__ x, long long ld, long long col_off, const QkvSegArgs a,
     const float* __restrict__ cosT, const float* __restrict__ sinT, __nv_bfloat16* __restrict__ dx, long long ld_dx,
     long long dx_col_off, int S, int H, float eps) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int D = H * 64;
     const int row = blockIdx.x;
     const int b = row / S, s = row % S;

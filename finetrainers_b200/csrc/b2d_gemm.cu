@@ -250,6 +250,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmKParams& p, int mt,
 
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmKParams p) {
+    griddep_launch_dependents();
     using Cfg = GemmCfg<BN, B_MN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();  // everything above touched only shared / tensor memory and kernel parameters
 
     const int kb_total = p.kb_main + p.kb_ext;  // per work item when splits == 1
     const int kb_per_split = (p.kb_main + p.splits - 1) / p.splits;
@@ -465,6 +467,7 @@ struct Gemm2Cfg {
 
 template <int BN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm2_kernel(const __grid_constant__ GemmKParams p) {
+    griddep_launch_dependents();
     using Cfg = Gemm2Cfg<BN, B_MN>;
     constexpr int HALF = Cfg::HALF;
     constexpr int NBOX = (HALF + 63) / 64;  // MN-major B: 64-column boxes per CTA
@@ -507,6 +510,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm2_kernel(const __grid_con
     cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / credited TMA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();  // everything above touched only shared / tensor memory and kernel parameters
 
     const int m_pairs = (p.m_tiles + 1) / 2;
     const int total = m_pairs * p.n_tiles * p.batch;

@@ -40,8 +40,14 @@ inline cudaError_t launch_kc(void (*kern)(P...), dim3 grid, dim3 block, size_t s
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     int n = 0;
+    // programmatic dependent launch (b2d_ptx.cuh: griddep_*): every kernel launched here calls griddep_wait()
+#ifndef B2D_NO_PDL
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+#endif
     if (cluster_x > 1) {
         at[n].id = cudaLaunchAttributeClusterDimension;
         at[n].val.clusterDim.x = (unsigned)cluster_x;

@@ -186,6 +186,20 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
 }
 
+// Programmatic dependent launch.  Every kernel launched through launch_k / launch_kc carries the programmatic-stream-
+// serialization attribute, so the NEXT kernel in the stream (or graph) may be scheduled onto SMs as soon as every CTA of
+// this grid has executed griddep_launch_dependents() (first statement of each kernel) and resources free up: its launch
+// latency and prologue (barrier init, tensor-memory allocation, descriptor prefetch) overlap this grid's tail.
+// griddep_wait() blocks until every prerequisite grid has COMPLETED and its memory is visible; each kernel executes it
+// before its first global-memory access (reads of earlier results, and writes that earlier kernels might still read).
+#ifndef B2D_NO_PDL  // (A/B builds only: tools/pdl_ab.sh)
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#else
+__device__ __forceinline__ void griddep_launch_dependents() {}
+__device__ __forceinline__ void griddep_wait() {}
+#endif
+
 // 256-bit store (sm_100 STG.256): one full 32-byte sector per lane.  One thread owns a row here, so a warp-wide 16-byte
 // store leaves 32 half-written sectors behind; the 32-byte form halves both the store instructions and the L2 write requests.
 __device__ __forceinline__ void st_global_32B(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
