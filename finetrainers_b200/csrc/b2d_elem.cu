@@ -613,28 +613,45 @@ __global__ void __launch_bounds__(ROW_THREADS) sumsq_kernel(const float* __restr
 }
 
 // clip (utils/torch.py:99-161: coef = min(1, max_norm / (norm + 1e-6))) + AdamW (torch.optim.AdamW math) + zero grad
-__global__ void adamw_clip_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                                  float* __restrict__ v, long long n, const float* __restrict__ sumsq, float max_norm,
-                                  float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
-                                  float grad_div) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ void adamw_one(float& pi, float& gi_io, float& mi, float& vi, float coef, float lr, float b1,
+                                          float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+    const float gi = gi_io * coef;
+    pi *= (1.f - lr * wd);
+    mi = b1 * mi + (1.f - b1) * gi;
+    vi = b2 * vi + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    gi_io = 0.f;
+}
+
+// four elements per thread as 16-byte accesses (7 streams of 4 B per element: the kernel is pure HBM traffic, and with one
+// element per thread it ran at ~60 % of the copy bandwidth); n4 = n / 4 vectors, the < 4-element tail goes to the last thread
+__global__ void __launch_bounds__(256) adamw_clip_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, long long n, const float* __restrict__ sumsq,
+                                                         float max_norm, float lr, float b1, float b2, float eps, float wd,
+                                                         float bc1, float bc2_sqrt, float grad_div) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n4 = n >> 2;
     float coef = grad_div;
     if (max_norm > 0.f) {
         float norm = sqrtf(*sumsq) * grad_div;
         coef *= fminf(1.f, max_norm / (norm + 1e-6f));
     }
-    float gi = g[i] * coef;
-    float pi = p[i];
-    pi *= (1.f - lr * wd);
-    float mi = b1 * m[i] + (1.f - b1) * gi;
-    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    float denom = sqrtf(vi) / bc2_sqrt + eps;
-    pi -= (lr / bc1) * (mi / denom);
-    p[i] = pi;
-    m[i] = mi;
-    v[i] = vi;
-    g[i] = 0.f;
+    if (i < n4) {
+        float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<float4*>(g)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        adamw_one(pp.x, gg.x, mm.x, vv.x, coef, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+        adamw_one(pp.y, gg.y, mm.y, vv.y, coef, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+        adamw_one(pp.z, gg.z, mm.z, vv.z, coef, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+        adamw_one(pp.w, gg.w, mm.w, vv.w, coef, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(g)[i] = gg;
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    if (i == n4) {
+        for (long long j = n4 << 2; j < n; ++j) adamw_one(p[j], g[j], m[j], v[j], coef, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+    }
 }
 
 }  // namespace b2d
@@ -852,8 +869,11 @@ extern "C" int b2d_adamw_clip(float* p, float* g, float* m, float* v, int64_t n,
     if (n <= 0) return 0;
     float bc1 = 1.f - powf(beta1, (float)step);
     float bc2s = sqrtf(1.f - powf(beta2, (float)step));
-    adamw_clip_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(p, g, m, v, n, sumsq, max_norm, lr, beta1, beta2,
-                                                                        eps, wd, bc1, bc2s, grad_div);
+    if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+         reinterpret_cast<uintptr_t>(v)) & 15)
+        return set_error(B2D_ERR_ALIGN, "adamw_clip: p, g, m, v must be 16-byte aligned");
+    adamw_clip_kernel<<<(unsigned)((n / 4 + 1 + 255) / 256), 256, 0, STREAM>>>(p, g, m, v, n, sumsq, max_norm, lr, beta1,
+                                                                                beta2, eps, wd, bc1, bc2s, grad_div);
     B2D_CHECK_LAUNCH("adamw_clip");
     return 0;
 }

@@ -184,6 +184,7 @@ int b2d_cast_f32_bf16(const float* src, void* dst, int64_t n, float scale, void*
  * Flat-buffer optimiser path ("next" row: clip + AdamW; finetrainers/utils/torch.py:99-161, optimizer.py:117-125).
  * ------------------------------------------------------------------------------------------------------------- */
 int b2d_sumsq(const float* x, int64_t n, float* out_sumsq /* += */, float* partial_ws, void* stream);
+/* p, g, m, v: 16-byte aligned (any n; four elements per thread as 128-bit accesses); g is zeroed (fused zero_grad). */
 int b2d_adamw_clip(float* p, float* g, float* m, float* v, int64_t n, const float* sumsq, float max_norm, float lr,
                    float beta1, float beta2, float eps, float wd, int32_t step, float grad_div, void* stream);
 
