@@ -26,6 +26,44 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert so.b2d_version() == 1
 
 
+def test_every_dependent_launch_kernel_waits_for_its_predecessors():
+    """launch_k / launch_kc attach the programmatic-dependent-launch attribute: a kernel launched through them may start
+    while its predecessor is still running, so EVERY such kernel must execute griddep_wait() before it touches global
+    memory (and griddep_launch_dependents() so that the scheme has an effect).  A kernel added later without the wait would
+    be a silent race; this keeps the source honest."""
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "finetrainers_b200", "csrc")
+    src = {f: open(os.path.join(root, f)).read() for f in os.listdir(root) if f.endswith(".cu")}
+    launched = set()
+    for text in src.values():
+        for m in re.finditer(r"launch_kc?\(\s*([A-Za-z_][A-Za-z0-9_]*)", text):
+            launched.add(m.group(1))
+    launched.discard("kern")            # launch_gemm / launch_gemm2 pass the instantiated template through a local
+    launched.update({"gemm_kernel", "gemm2_kernel"})
+    if "KERNEL" in launched:            # ROW_DISPATCH(D, KERNEL, ...) macro: collect its instantiations
+        launched.discard("KERNEL")
+        for text in src.values():
+            launched.update(re.findall(r"ROW_DISPATCH\([^,]+,\s*([A-Za-z_][A-Za-z0-9_]*)", text))
+    launched.discard("KERNEL")
+    assert len(launched) >= 12, launched
+    allsrc = "\n".join(src.values())
+    for k in sorted(launched):
+        m = re.search(r"__global__[^;{]*\b" + k + r"\s*\(", allsrc)
+        assert m, f"kernel {k} not found"
+        # function body: from the first '{' after the signature to the matching '}'
+        i = allsrc.index("{", allsrc.index(")", m.end()))
+        depth, j = 0, i
+        while True:
+            c = allsrc[j]
+            depth += c == "{"
+            depth -= c == "}"
+            if depth == 0:
+                break
+            j += 1
+        body = allsrc[i:j]
+        assert "griddep_wait()" in body, f"{k} is launched with the dependent-launch attribute but never waits"
+        assert "griddep_launch_dependents()" in body, f"{k} never releases its dependents early"
+
+
 def test_ops_fail_loudly_without_cuda():
     from finetrainers_b200 import ops, lib
     x = torch.zeros(8, 8, dtype=torch.bfloat16)
