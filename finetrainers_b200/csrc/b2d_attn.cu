@@ -455,29 +455,17 @@ static_assert(PP_TY % 16 == 0 && PP_TY <= 64, "tile width: whole k-steps, at mos
 constexpr int PP_SMEM = 2 * TILE_BYTES + PP_STAGES * 2 * PP_Y_BYTES + PP_STAGES * 2 * PP_TY * 4 + 1024 + 256;
 
 // One tcgen05.ld chunk of NC (32 or 16) score columns starting at column c0 of this thread's row: P = exp2(S*scale + a),
-// dS = P * (dP - d) with the per-column terms a / d read from shared memory (or absent: no_col), written back as bf16
+// dS = P * (dP - d) with the per-column terms a / d read from shared memory, written back as bf16
 // pairs over columns [c0/2, c0/2 + NC/2) of the same S / dP buffers.
 template <bool DKV, int NC>
-__device__ __forceinline__ void pp_consume(uint32_t tS, uint32_t tDP, int c0, uint32_t aCA, uint32_t aCD, bool no_col,
+__device__ __forceinline__ void pp_consume(uint32_t tS, uint32_t tDP, int c0, uint32_t aCA, uint32_t aCD,
                                            bool add_row, float rowA, float rowD, float scale_log2) {
     uint32_t sv[NC], dv[NC];
     tmem_ld_n<NC>(tS + c0, sv);
     tmem_ld_n<NC>(tDP + c0, dv);
     float pe[NC], ds[NC];
     const uint64_t scale2 = f2_pack(scale_log2, scale_log2);
-    if (no_col) {
-        const uint64_t rowA2 = f2_pack(rowA, rowA), rowD2 = f2_pack(rowD, rowD);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < NC; e += 2) {
-            float x0, x1;
-            f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), scale2, rowA2), x0, x1);
-            pe[e] = fast_exp2(x0);
-            pe[e + 1] = fast_exp2(x1);
-            const uint64_t t2 = f2_sub(f2_pack(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), rowD2);
-            f2_unpack(f2_mul(f2_pack(pe[e], pe[e + 1]), t2), ds[e], ds[e + 1]);
-        }
-    } else {
+    {
         float ca[NC], cd[NC];
 #pragma unroll
         for (int u = 0; u < NC / 4; ++u) {
@@ -668,8 +656,13 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             float* cD = sColD + st * TY;
             const bool full_tile = (i + 1) * TY <= rowsY;
             const bool col_by_copy = DKV && full_tile && ((rowsY & 3) == 0);
-            const bool no_col = !DKV && full_tile && (p.key_bias == nullptr);
-            if (!col_by_copy && !no_col) {
+            // The dQ pass used to skip the column vectors on full tiles without a key bias (a branch of pp_consume that took
+            // only the per-row terms).  A soak of the full-size training step showed that branch producing a few rows of garbage
+            // dQ (|values| ~ 1e37, some inf / NaN) once every ~20 optimizer steps, not reproducible on the same inputs; with the
+            // dQ pass on the column-vector path - the one the dK/dV pass has always used - 150 steps / 8400 calls were clean
+            // (profiles/r2b_attention_backward_nan.md).  The branch is gone; the cost is one 48-float shared-memory fill and a
+            // named barrier per tile.
+            if (!col_by_copy) {
                 if (tid128 < TY) {
                     const int ycol = i * TY + tid128;
                     const bool ok = ycol < rowsY;
@@ -691,8 +684,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             const bool add_row = !DKV || p.key_bias != nullptr || !row_ok;
             // 48 columns = one 32-column and one 16-column tcgen05.ld chunk; chunk c's bf16 pairs land in columns
             // [c0 / 2, c0 / 2 + NC / 2) of the S (resp. dP) buffer: columns this thread has already read
-            pp_consume<DKV, 32>(tS, tDP, 0, aCA, aCD, no_col, add_row, rowA, rowD, p.scale_log2);
-            if (TY > 32) pp_consume<DKV, (TY > 32 ? TY - 32 : 16)>(tS, tDP, 32, aCA, aCD, no_col, add_row, rowA, rowD, p.scale_log2);
+            pp_consume<DKV, 32>(tS, tDP, 0, aCA, aCD, add_row, rowA, rowD, p.scale_log2);
+            if (TY > 32) pp_consume<DKV, (TY > 32 ? TY - 32 : 16)>(tS, tDP, 32, aCA, aCD, add_row, rowA, rowD, p.scale_log2);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&ds_full[wg]);

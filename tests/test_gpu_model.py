@@ -344,3 +344,42 @@ def test_three_step_trajectory_first_frame_conditioning_and_lr_schedule():
             assert cos > 0.95 and abs(db.norm() / do.norm() - 1) < 0.05, (n, cos.item(), (db.norm() / do.norm()).item())
             checked += 1
     assert checked >= 30
+
+
+@pytest.mark.timeout(600)
+def test_full_size_soak_gradients_stay_finite_and_sane():
+    """40 optimizer steps of the full-size model (28 blocks, 2688 tokens), eager, metrics read every step: the gradient norm
+    must stay finite and of order one.  This is the test that was missing when the dQ pass of the attention backward had a
+    branch that produced a few rows of garbage (|dq| ~ 1e37, some inf / NaN) once every ~20 steps - invisible to every
+    single-step parity test and to the bench, fatal to a real run (profiles/r2b_attention_backward_nan.md).  Before the fix
+    a 40-step run failed with probability ~0.85."""
+    from finetrainers_b200.model import B200LTXTransformer, LTXConfig
+    from finetrainers_b200.trainer import SFTTrainStep
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    model = B200LTXTransformer(LTXConfig(), torch.bfloat16, dev)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if "scale_shift_table" in name:
+                p.normal_(0, 1.0 / p.shape[-1] ** 0.5)
+            elif "norm_q" in name or "norm_k" in name:
+                p.fill_(1.0)
+            else:
+                p.normal_(0, 0.02)
+    model.add_adapter(64, 64)
+    model.prepare()
+    st = SFTTrainStep(model, use_cuda_graph=False, lr=1e-4, seed=7)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    lat = torch.randn(4, 1, 128, 7, 16, 24, generator=g).bfloat16().to(dev)
+    ehs = (torch.randn(4, 1, 128, 4096, generator=g) * 0.1).bfloat16().to(dev)
+    mask = torch.arange(128, device=dev)[None] < 77
+    mean, std = torch.zeros(1, 128, device=dev), torch.ones(1, 128, device=dev)
+    for i in range(40):
+        m = st.train_step({"encoder_hidden_states": ehs[i % 4], "encoder_attention_mask": mask},
+                          {"latents": lat[i % 4], "latents_mean": mean, "latents_std": std}, sync_metrics=True)
+        loss, gn = m["train/global_avg_loss"], m["train/grad_norm"]
+        assert loss == loss and 0.5 < loss < 10.0, (i, loss)
+        assert gn == gn and 1e-3 < gn < 10.0, (i, gn)
+    assert torch.isfinite(model.lora_flat).all()
+    del st, model
+    torch.cuda.empty_cache()
