@@ -18,6 +18,7 @@ PyTorch SDPA and per-block activation checkpointing - the "PyTorch eager on the 
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import sys
@@ -324,13 +325,20 @@ def run_b200(args):
         step.train_step({"encoder_hidden_states": ehs, "encoder_attention_mask": mask},
                         {"latents": lat, "latents_mean": mean, "latents_std": std})
 
+    last_metrics = {}
+
     def step_e2e(i):
         lat, ehs, mask = pool[i % len(pool)]
         lat_d = lat.to(dev, non_blocking=True)
         ehs_d = ehs.to(dev, non_blocking=True)
         mask_d = mask.to(dev, non_blocking=True)
-        return step.train_step({"encoder_hidden_states": ehs_d, "encoder_attention_mask": mask_d},
-                               {"latents": lat_d, "latents_mean": mean, "latents_std": std}, sync_metrics=True)
+        m = step.train_step({"encoder_hidden_states": ehs_d, "encoder_attention_mask": mask_d},
+                            {"latents": lat_d, "latents_mean": mean, "latents_std": std}, sync_metrics=True)
+        last_metrics.update(m)
+        # a throughput measured on garbage is not a measurement: stop at the first non-finite loss / gradient norm
+        if not (math.isfinite(m["train/global_avg_loss"]) and math.isfinite(m["train/grad_norm"])):
+            raise SystemExit(f"bench: non-finite training metrics at e2e step {i}: {m}")
+        return m
 
     def barrier():
         if world > 1:
@@ -463,6 +471,7 @@ def run_b200(args):
                 "ms_per_step": ms_e2e / args.steps, "ms_per_step_median": statistics.median(per_e2e)},
         "consistency": {"value_vs_e2e_rel_diff": abs(ms_total - ms_e2e) / ms_total, "remeasured": remeasured},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "final_metrics": {"loss": last_metrics.get("train/global_avg_loss"), "grad_norm": last_metrics.get("train/grad_norm")},
         "cuda_graph": step.use_cuda_graph,
     }
     if fsdp:
