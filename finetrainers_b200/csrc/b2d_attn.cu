@@ -656,12 +656,16 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
             float* cD = sColD + st * TY;
             const bool full_tile = (i + 1) * TY <= rowsY;
             const bool col_by_copy = DKV && full_tile && ((rowsY & 3) == 0);
-            // The dQ pass used to skip the column vectors on full tiles without a key bias (a branch of pp_consume that took
-            // only the per-row terms).  A soak of the full-size training step showed that branch producing a few rows of garbage
-            // dQ (|values| ~ 1e37, some inf / NaN) once every ~20 optimizer steps, not reproducible on the same inputs; with the
-            // dQ pass on the column-vector path - the one the dK/dV pass has always used - 150 steps / 8400 calls were clean
-            // (profiles/r2b_attention_backward_nan.md).  The branch is gone; the cost is one 48-float shared-memory fill and a
-            // named barrier per tile.
+            // Every tile starts with a barrier over this warpgroup's four warps (inside the fill path, or on its own).  It is
+            // what makes the 128-arrival ds_full[wg] barrier sound: with more S/dP buffers than warpgroups, S/dP(it + 3) does
+            // NOT depend on this warpgroup's tile `it` having been released, so a warp that ran ahead could consume tile
+            // it + 3 and arrive on ds_full[wg] a SECOND time before a delayed sibling warp had arrived for tile `it` - the
+            // phase then completed with that warp's rows of P^T / dS^T still holding the fp32 S / dP bits, and the
+            // accumulation GEMM read them as bf16 pairs.  Observed in the dQ pass (whose full unbiased tiles used to skip this
+            // block): a few rows of one warp's lane range with |dq| ~ 1e37 about once per 600 calls, NaN loss within ~50
+            // training steps; 150 steps / 8400 calls clean once every dQ tile went through the barrier
+            // (profiles/r2b_attention_backward_nan.md).  The dK/dV pass has the same exposure on its bulk-copy path, hence the
+            // unconditional barrier.
             if (!col_by_copy) {
                 if (tid128 < TY) {
                     const int ycol = i * TY + tid128;
@@ -674,6 +678,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_pp_kernel(const __grid
                         cD[tid128] = 0.f;
                     }
                 }
+                named_bar_sync(1 + wg, 128);
+            } else {
                 named_bar_sync(1 + wg, 128);
             }
             if (col_by_copy) mbar_wait(&y_full[st], (uint32_t)((it / PP_STAGES) & 1));
