@@ -427,7 +427,8 @@ struct AttnBwdParams {
 // columns of dV/dK or dQ accumulators = all 512) for THREE consumer warpgroups, which take 48-row tiles round-robin.
 // One more buffer than warpgroups is what decouples them from the tensor pipe: the S/dP of a warpgroup's NEXT tile
 // (it + 3, buffer (it + 3) % 4) is issued when tile it - 1 is released, i.e. while the warpgroup is still working on
-// tile it.  With one buffer per warpgroup (3 x 128 columns, 64-row tiles) a clock64 trace showed every warpgroup
+// tile it.  (It also means that the 128-arrival release barrier of a warpgroup needs a warpgroup-wide barrier at the start
+// of every tile: see the consumer loop.)  With one buffer per warpgroup (3 x 128 columns, 64-row tiles) a clock64 trace showed every warpgroup
 // waiting ~1000 of its ~2500 cycles per tile for "its" S/dP to be recomputed (profiles/r2_attention_phase_trace_*).  Three warpgroups (one per accumulator buffer) put three consumer
 // warps on every SM sub-partition: a tile costs a warp 64 MUFU.EX2 issues (512 cycles of its sub-partition's XU) plus
 // tcgen05.ld / pack / tcgen05.st / barrier phases during which it issues none, and with only two warps per
