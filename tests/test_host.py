@@ -64,6 +64,23 @@ def test_every_dependent_launch_kernel_waits_for_its_predecessors():
         assert "griddep_launch_dependents()" in body, f"{k} never releases its dependents early"
 
 
+def test_attention_backward_consumers_synchronise_every_tile():
+    """attn_bwd_pp_kernel releases a tile on a 128-arrival mbarrier shared by tiles it and it + 3 of a warpgroup, while the
+    S/dP of tile it + 3 does not wait for that release (four buffers, three warpgroups).  Without a warpgroup-wide barrier at
+    the start of every tile a warp can arrive twice before a sibling arrives once, and the accumulation GEMM reads rows that
+    were never written (profiles/r2b_attention_backward_nan.md: garbage dQ about once per 600 calls).  Both paths of the
+    consumer loop must therefore end in the named barrier."""
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "finetrainers_b200", "csrc")
+    text = open(os.path.join(root, "b2d_attn.cu")).read()
+    i = text.index("for (int it = wg; it < n_y; it += PP_NWG) {")
+    j = text.index("mbar_arrive(&ds_full[wg]);", i)
+    body = text[i:j]
+    m = re.search(r"if \(!col_by_copy\) \{(.*?)\} else \{(.*?)\}", body, re.S)
+    assert m, "consumer loop: expected the fill path / bulk-copy path pair"
+    assert "named_bar_sync(1 + wg, 128);" in m.group(1) and "named_bar_sync(1 + wg, 128);" in m.group(2)
+    assert body.index("named_bar_sync(1 + wg, 128);") < body.index("mbar_wait(&s_full[kb]")
+
+
 def test_ops_fail_loudly_without_cuda():
     from finetrainers_b200 import ops, lib
     x = torch.zeros(8, 8, dtype=torch.bfloat16)
