@@ -75,10 +75,11 @@ def test_attention_backward_consumers_synchronise_every_tile():
     i = text.index("for (int it = wg; it < n_y; it += PP_NWG) {")
     j = text.index("mbar_arrive(&ds_full[wg]);", i)
     body = text[i:j]
-    m = re.search(r"if \(!col_by_copy\) \{(.*?)\} else \{(.*?)\}", body, re.S)
-    assert m, "consumer loop: expected the fill path / bulk-copy path pair"
-    assert "named_bar_sync(1 + wg, 128);" in m.group(1) and "named_bar_sync(1 + wg, 128);" in m.group(2)
-    assert body.index("named_bar_sync(1 + wg, 128);") < body.index("mbar_wait(&s_full[kb]")
+    head = body[:body.index("mbar_wait(&s_full[kb]")]                   # everything before the tile's S/dP is awaited
+    assert "if (!col_by_copy) {" in head
+    assert head.count("named_bar_sync(1 + wg, 128);") == 2, "one barrier on the fill path, one on the bulk-copy path"
+    assert re.search(r"named_bar_sync\(1 \+ wg, 128\);\s*\} else \{\s*named_bar_sync\(1 \+ wg, 128\);\s*\}", head), \
+        "the two barriers must be the last statement of the if-branch and the whole else-branch"
 
 
 def test_ops_fail_loudly_without_cuda():
