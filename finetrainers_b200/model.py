@@ -331,9 +331,11 @@ class B200LTXTransformer(nn.Module):
         os.makedirs(directory, exist_ok=True)
         sd = {"transformer." + k: v for k, v in self.lora_state_dict().items()}
         tm = getattr(self, "_lora_targets", LORA_TARGETS)
+        # same keys, order and formatting as the reference's save hook (trainer.py:284-290)
         meta = {"format": "pt", "lora_config": json.dumps({"r": self.lora_rank, "lora_alpha": self.lora_rank * self.lora_scaling,
-                                                           "target_modules": tm if isinstance(tm, str) else list(tm),
-                                                           "init_lora_weights": getattr(self, "_lora_init", True)})}
+                                                           "init_lora_weights": getattr(self, "_lora_init", True),
+                                                           "target_modules": tm if isinstance(tm, str) else list(tm)},
+                                                          indent=4)}
         meta.update(metadata or {})
         path = os.path.join(directory, "pytorch_lora_weights.safetensors")
         save_file(sd, path, metadata=meta)
